@@ -1,0 +1,153 @@
+"""Thin Python wrappers: PyTorch tensors in, PyTorch tensors out, math in libbioreason_b200 (C ABI).
+
+PyTorch here is plumbing only: it owns device memory and streams.  Every op raises if its tensors
+are not CUDA tensors -- there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from ._lib import check, ffi, lib, ptr
+
+BF16, F32 = 0, 1
+
+
+def _stream():
+    return ffi.cast("void*", torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("bioreason_b200 ops run on CUDA tensors only (no CPU fallback)")
+
+
+# ------------------------------------------------------------------ GRPO
+def grpo_advantages(rewards_per_func: torch.Tensor, num_generations: int, return_stats: bool = False):
+    """grpo_trainer.py:682-692."""
+    _need_cuda(rewards_per_func)
+    r = rewards_per_func.float().contiguous()
+    rows, nf = r.shape
+    adv = torch.empty(rows, device=r.device, dtype=torch.float32)
+    gm = torch.empty(rows // num_generations, device=r.device, dtype=torch.float32)
+    gs = torch.empty_like(gm)
+    check(lib().br_grpo_advantages(ptr(r, "float*"), rows, nf, num_generations, ptr(adv, "float*"),
+                                   ptr(gm, "float*"), ptr(gs, "float*"), _stream()), "grpo_advantages")
+    return (adv, gm, gs) if return_stats else adv
+
+
+def grpo_loss_raw(lp, old_lp, ref_lp, adv, mask, beta, eps_low, eps_high, want_grad=True):
+    _need_cuda(lp, adv, mask)
+    B, C = lp.shape
+    lp = lp.float().contiguous()
+    old_lp = None if old_lp is None else old_lp.float().contiguous()
+    ref_lp = None if ref_lp is None else ref_lp.float().contiguous()
+    adv = adv.float().contiguous()
+    mask = mask.to(torch.int32).contiguous()
+    out3 = torch.empty(3, device=lp.device, dtype=torch.float32)
+    dlp = torch.empty_like(lp) if want_grad else None
+    check(lib().br_grpo_loss_fwd_bwd(ptr(lp, "float*"), ptr(old_lp, "float*"), ptr(ref_lp, "float*"), ptr(adv, "float*"),
+                                     ptr(mask, "int32_t*"), B, C, float(beta), float(eps_low), float(eps_high),
+                                     ptr(out3, "float*"), ptr(dlp, "float*"), _stream()), "grpo_loss")
+    return out3, dlp
+
+
+class _GRPOLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lp, old_lp, ref_lp, adv, mask, beta, eps_low, eps_high):
+        out3, dlp = grpo_loss_raw(lp.detach(), old_lp, ref_lp, adv, mask, beta, eps_low, eps_high)
+        ctx.save_for_backward(dlp)
+        ctx.mark_non_differentiable(out3)
+        return out3[0].clone(), out3
+
+    @staticmethod
+    def backward(ctx, g, _g3):
+        (dlp,) = ctx.saved_tensors
+        return dlp * g, None, None, None, None, None, None, None
+
+
+def grpo_loss(lp, old_lp, ref_lp, adv, mask, beta=0.04, eps_low=0.2, eps_high=0.2):
+    """grpo_trainer.py:786-812 -> (loss, out3=[loss, mean_kl, clip_ratio]); differentiable w.r.t. lp."""
+    return _GRPOLoss.apply(lp, old_lp, ref_lp, adv, mask, beta, eps_low, eps_high)
+
+
+def eos_mask(completion_ids: torch.Tensor, eos_id: int) -> torch.Tensor:
+    """grpo_trainer.py:605-609."""
+    _need_cuda(completion_ids)
+    ids = completion_ids.to(torch.int64).contiguous()
+    B, C = ids.shape
+    m = torch.empty(B, C, device=ids.device, dtype=torch.int32)
+    check(lib().br_eos_mask(ptr(ids, "int64_t*"), B, C, int(eos_id), ptr(m, "int32_t*"), _stream()), "eos_mask")
+    return m
+
+
+# ------------------------------------------------------------------ GEMM
+def _row_major_2d(t):
+    assert t.dim() == 2 and t.stride(1) == 1, "need a 2-D tensor with contiguous last dim"
+    return t.stride(0)
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, *, bias=None, residual=None, alpha: float = 1.0, act: int = 0,
+         out: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16, row_map=None, aux_out=None,
+         a2=None, b2=None) -> torch.Tensor:
+    """out[M,N] = epilogue(a[M,K] @ b[N,K].T (+ a2[M,K2] @ b2[N,K2].T)) on tcgen05 (bf16 in, fp32 accumulate)."""
+    _need_cuda(a, b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    M, K = a.shape
+    N, Kb = b.shape
+    assert K == Kb
+    n_out = N // 2 if act == 1 else N
+    if out is None:
+        out = torch.empty(M, n_out, device=a.device, dtype=out_dtype)
+    e = ffi.new("br_gemm_epilogue*")
+    e.alpha = alpha
+    e.act = act
+    e.out_dtype = F32 if out.dtype == torch.float32 else BF16
+    keep = [a, b, out]
+    if bias is not None:
+        e.bias = ptr(bias); e.bias_dtype = F32 if bias.dtype == torch.float32 else BF16; keep.append(bias)
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16
+        e.residual = ptr(residual); e.ldr = _row_major_2d(residual); keep.append(residual)
+    if row_map is not None:
+        assert row_map.dtype == torch.int32
+        e.row_map = ptr(row_map, "int32_t*"); keep.append(row_map)
+    if aux_out is not None:
+        e.aux_out = ptr(aux_out); e.ld_aux = _row_major_2d(aux_out); keep.append(aux_out)
+    if a2 is not None:
+        assert a2.dtype == torch.bfloat16 and b2.dtype == torch.bfloat16 and a2.shape[0] == M and b2.shape[0] == N
+        e.A2 = ptr(a2); e.lda2 = _row_major_2d(a2); e.B2 = ptr(b2); e.ldb2 = _row_major_2d(b2); e.K2 = a2.shape[1]
+        keep += [a2, b2]
+    check(lib().br_gemm_bf16(ptr(a), _row_major_2d(a), ptr(b), _row_major_2d(b), ptr(out), _row_major_2d(out),
+                             M, N, K, e, _stream()), "gemm_bf16")
+    return out
+
+
+def lmhead_logprob(h: torch.Tensor, w: torch.Tensor, target: torch.Tensor, scale: float = 1.0):
+    """Fused lm_head + log_softmax + gather (grpo_trainer.py:511-520): returns (logp[M], lse[M]) fp32."""
+    _need_cuda(h, w, target)
+    M, K = h.shape
+    V = w.shape[0]
+    tgt = target.to(torch.int32).contiguous()
+    ws = torch.empty(lib().br_lmhead_workspace_bytes(M, V), device=h.device, dtype=torch.uint8)
+    logp = torch.empty(M, device=h.device, dtype=torch.float32)
+    lse = torch.empty(M, device=h.device, dtype=torch.float32)
+    check(lib().br_lmhead_logprob_fwd(ptr(h), _row_major_2d(h), ptr(w), _row_major_2d(w), ptr(tgt, "int32_t*"), M, V, K,
+                                      float(scale), ptr(logp, "float*"), ptr(lse, "float*"), ptr(ws), _stream()),
+          "lmhead_logprob_fwd")
+    return logp, lse
+
+
+def lmhead_dlogits(h, w, target, lse, gscale, scale: float = 1.0):
+    """bf16 [M, V] tile-recomputed gradient of sum_m gscale[m] * logp[m] w.r.t. the logits."""
+    _need_cuda(h, w, target)
+    M, K = h.shape
+    V = w.shape[0]
+    tgt = target.to(torch.int32).contiguous()
+    d = torch.empty(M, V, device=h.device, dtype=torch.bfloat16)
+    check(lib().br_lmhead_dlogits(ptr(h), _row_major_2d(h), ptr(w), _row_major_2d(w), ptr(tgt, "int32_t*"),
+                                  ptr(lse, "float*"), ptr(gscale.float().contiguous(), "float*"), M, V, K, float(scale),
+                                  ptr(d), V, _stream()), "lmhead_dlogits")
+    return d

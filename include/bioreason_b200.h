@@ -1,0 +1,87 @@
+/* libbioreason_b200 -- C ABI of the B200-native BioReason hot path.
+ *
+ * The reference (bowang-lab/BioReason) has no FFI: its hot path is Python calling HuggingFace/PyTorch
+ * (SURVEY.md §8b).  This header is the boundary the build introduces *below* the reference's Python
+ * surface (`DNALLMModel`, `DNALLMGRPOTrainer`); each entry point names the reference call site it
+ * replaces.  Conventions:
+ *   - plain pointers + sizes, no torch types; every pointer is a CUDA device pointer unless noted;
+ *   - every call enqueues on `stream` (a cudaStream_t) and returns without synchronising;
+ *   - return 0 on success, <0 on error; `br_last_error()` gives the (thread-local) message;
+ *   - the caller (PyTorch) owns all buffers; the library keeps no pointer past the call, except the
+ *     NCCL communicator handle (`br_comm_*`);
+ *   - bf16 = __nv_bfloat16 storage, fp32 accumulation everywhere.
+ * This file is parsed by cffi (ABI mode): keep it plain C, no macros beyond the constants below.
+ */
+#ifndef BIOREASON_B200_H
+#define BIOREASON_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BR_BF16 0
+#define BR_F32 1
+
+int br_version(void);
+/* copies the calling thread's last error message into buf (NUL-terminated); returns its length */
+int br_last_error(char* buf, size_t n);
+/* 1 if the visible device is sm_100 (B200); the library refuses to run elsewhere */
+int br_device_ok(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * GRPO advantages + loss  (replaces bioreason/trainer/grpo_trainer.py:682-692 and :786-812)
+ * ------------------------------------------------------------------------------------------- */
+/* rewards_per_func [rows, n_funcs] f32 -> advantages [rows] f32; groups are G consecutive rows. */
+int br_grpo_advantages(const float* rewards_per_func, int rows, int n_funcs, int G, float* advantages,
+                       float* group_mean, float* group_std, void* stream);
+/* lp/old_lp/ref_lp [B, C] f32 (old_lp NULL => mu == 1; ref_lp NULL => beta == 0), adv [B], mask [B, C] int32.
+ * out3 = {loss, mean_kl, clip_ratio}; dlp [B, C] = d loss / d lp (may be NULL). One launch. */
+int br_grpo_loss_fwd_bwd(const float* lp, const float* old_lp, const float* ref_lp, const float* adv,
+                         const int32_t* mask, int B, int C, float beta, float eps_low, float eps_high,
+                         float* out3, float* dlp, void* stream);
+/* completion_mask[b, t] = t <= first_eos(b) (grpo_trainer.py:605-609); ids int64 [B, C] -> mask int32 */
+int br_eos_mask(const int64_t* completion_ids, int B, int C, int64_t eos_id, int32_t* mask, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense contractions on tcgen05 (replaces every nn.Linear / lm_head reached through
+ * dna_llm.py:150-160,237-242; SURVEY.md §2.3 K1,K2,K5,K6,K7,K12)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct br_gemm_epilogue {
+    const void* bias;        /* [N] or NULL */
+    int32_t bias_dtype;      /* BR_BF16 / BR_F32 */
+    const void* residual;    /* bf16 [M, ldr] added after bias (indexed by OUTPUT row) or NULL */
+    int64_t ldr;
+    float alpha;             /* scales the accumulator first */
+    int32_t act;             /* 0 none; 1: out[:, j] = silu(acc[:, 2j]) * acc[:, 2j+1]  (out width N/2) */
+    int32_t out_dtype;       /* BR_BF16 / BR_F32 */
+    const int32_t* row_map;  /* optional [M]: output row of input row m (<0: dropped) -- projector scatter */
+    void* aux_out;           /* act==1: optional bf16 [M, ld_aux] copy of the pre-activation accumulator */
+    int64_t ld_aux;
+    const void* A2;          /* optional second K segment accumulated into the same tile: */
+    int64_t lda2;            /*   D += A2[M, K2] . B2[N, K2]^T   (LoRA delta) */
+    const void* B2;
+    int64_t ldb2;
+    int32_t K2;
+} br_gemm_epilogue;
+
+/* D[M, N] = epilogue(A[M, K] . B[N, K]^T); A, B bf16 row-major (K contiguous); ld* in elements. */
+int br_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* D, int64_t ldd,
+                 int M, int N, int K, const br_gemm_epilogue* epi, void* stream);
+
+/* Fused lm_head + log-softmax + gather (replaces grpo_trainer.py:511-520 and HF loss_utils CE):
+ * logp[m] = scale*H[m].W[target[m]] - logsumexp_v(scale*H[m].W[v]); logits never reach HBM.
+ * target[m] < 0 => logp 0 (ignored row).  lse [M] is kept for the backward. */
+int64_t br_lmhead_workspace_bytes(int M, int V);
+int br_lmhead_logprob_fwd(const void* H, int64_t ldh, const void* W, int64_t ldw, const int32_t* target,
+                          int M, int V, int K, float scale, float* logp, float* lse, void* workspace, void* stream);
+/* dlogits[m, v] = gscale[m] * (onehot(target[m])[v] - softmax(H[m].W)[v]) as bf16 [M, ldd] (recomputed tiles) */
+int br_lmhead_dlogits(const void* H, int64_t ldh, const void* W, int64_t ldw, const int32_t* target,
+                      const float* lse, const float* gscale, int M, int V, int K, float scale,
+                      void* dlogits, int64_t ldd, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
