@@ -151,3 +151,80 @@ def lmhead_dlogits(h, w, target, lse, gscale, scale: float = 1.0):
                                   ptr(lse, "float*"), ptr(gscale.float().contiguous(), "float*"), M, V, K, float(scale),
                                   ptr(d), V, _stream()), "lmhead_dlogits")
     return d
+
+
+# ------------------------------------------------------------------ row kernels
+def rmsnorm(x, w, eps: float, out=None, want_rstd: bool = False):
+    _need_cuda(x, w)
+    M, d = x.shape
+    if out is None:
+        out = torch.empty(M, d, device=x.device, dtype=torch.bfloat16)
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32) if want_rstd else None
+    check(lib().br_rmsnorm(ptr(x), _row_major_2d(x), ptr(w), ptr(out), _row_major_2d(out), ptr(rstd, "float*"), M, d, float(eps),
+                           _stream()), "rmsnorm")
+    return (out, rstd) if want_rstd else out
+
+
+def layernorm(x, w, b, eps: float, out=None):
+    _need_cuda(x, w, b)
+    M, d = x.shape
+    if out is None:
+        out = torch.empty(M, d, device=x.device, dtype=torch.bfloat16)
+    check(lib().br_layernorm(ptr(x), _row_major_2d(x), ptr(w), ptr(b), ptr(out), _row_major_2d(out), M, d, float(eps), _stream()),
+          "layernorm")
+    return out
+
+
+def qk_rope_(qkv, n_q, n_k, head_dim, positions, theta, *, q_norm_w=None, k_norm_w=None, eps=1e-6, q_scale=1.0, mode=0):
+    """In place on the fused QKV buffer [M, >= (n_q+n_k)*head_dim]."""
+    _need_cuda(qkv, positions)
+    assert positions.dtype == torch.int32 and positions.numel() == qkv.shape[0]
+    check(lib().br_qk_rope(ptr(qkv), _row_major_2d(qkv), qkv.shape[0], n_q, n_k, head_dim, ptr(q_norm_w), ptr(k_norm_w),
+                           ptr(positions, "int32_t*"), float(theta), float(eps), float(q_scale), mode, _stream()), "qk_rope")
+    return qkv
+
+
+def embed_gather(ids, table, keep=None, out=None):
+    _need_cuda(ids, table)
+    ids = ids.reshape(-1).to(torch.int64).contiguous()
+    M, d = ids.numel(), table.shape[1]
+    if out is None:
+        out = torch.empty(M, d, device=table.device, dtype=torch.bfloat16)
+    if keep is not None:
+        keep = keep.reshape(-1).to(torch.int32).contiguous()
+    check(lib().br_embed_gather(ptr(ids, "int64_t*"), ptr(table), _row_major_2d(table), table.shape[0], ptr(out),
+                                _row_major_2d(out), M, d, ptr(keep, "int32_t*"), _stream()), "embed_gather")
+    return out
+
+
+def scatter_rows_(dst, src, row_map):
+    _need_cuda(dst, src, row_map)
+    assert row_map.dtype == torch.int32
+    check(lib().br_scatter_rows(ptr(src), _row_major_2d(src), ptr(row_map, "int32_t*"), ptr(dst), _row_major_2d(dst),
+                                src.shape[0], src.shape[1], _stream()), "scatter_rows")
+    return dst
+
+
+def gather_rows(src, idx, out=None):
+    _need_cuda(src, idx)
+    assert idx.dtype == torch.int32
+    if out is None:
+        out = torch.empty(idx.numel(), src.shape[1], device=src.device, dtype=torch.bfloat16)
+    check(lib().br_gather_rows(ptr(src), _row_major_2d(src), ptr(idx, "int32_t*"), ptr(out), _row_major_2d(out),
+                               idx.numel(), src.shape[1], _stream()), "gather_rows")
+    return out
+
+
+# ------------------------------------------------------------------ attention
+def attn_fwd(q, k, v, B, L, n_q, n_kv, head_dim, *, kv_start=None, kv_end=None, scale=None, causal=True, want_lse=False, out=None):
+    """q/k/v: 2-D views [B*L, heads*head_dim] (may alias one fused QKV buffer)."""
+    _need_cuda(q, k, v)
+    if out is None:
+        out = torch.empty(B * L, n_q * head_dim, device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty(B, n_q, L, device=q.device, dtype=torch.float32) if want_lse else None
+    if scale is None:
+        scale = head_dim ** -0.5
+    check(lib().br_attn_fwd(ptr(q), _row_major_2d(q), ptr(k), _row_major_2d(k), ptr(v), _row_major_2d(v), ptr(out), _row_major_2d(out),
+                            ptr(lse, "float*"), B, L, n_q, n_kv, head_dim, ptr(kv_start, "int32_t*"), ptr(kv_end, "int32_t*"),
+                            float(scale), 1 if causal else 0, _stream()), "attn_fwd")
+    return (out, lse) if want_lse else out

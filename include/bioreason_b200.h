@@ -81,6 +81,35 @@ int br_lmhead_dlogits(const void* H, int64_t ldh, const void* W, int64_t ldw, co
                       const float* lse, const float* gscale, int M, int V, int K, float scale,
                       void* dlogits, int64_t ldd, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Row kernels (HBM-bound): norms, rotary, gathers  (replace HF Qwen3RMSNorm qwen3/modeling_qwen3.py:50-64,
+ * torch LayerNorm in esm/modeling_esm.py:386-400,476-479,511, apply_rotary_pos_emb qwen3:120-150 / esm:45-55,
+ * embed_tokens + masked scatter dna_llm.py:211-229)
+ * ------------------------------------------------------------------------------------------- */
+/* y = w * bf16(x * rsqrt(mean(x^2)+eps)); bf16 [M, d]; rstd [M] f32 optional (kept for the backward) */
+int br_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, float* rstd, int M, int d, float eps, void* stream);
+int br_layernorm(const void* x, int64_t ldx, const void* w, const void* b, void* y, int64_t ldy, int M, int d, float eps, void* stream);
+/* In place on the fused QKV activation [M, ld]: heads 0..n_q-1 are queries, the next n_k are keys.
+ * mode 0 (Qwen3): per-head RMSNorm with q_norm_w / k_norm_w [head_dim] (NULL = skip) then rotate-half RoPE;
+ * mode 1 (ESM/NT-v2): queries scaled by q_scale, then RoPE.  positions [M] int32 (explicit: the reference uses
+ * arange over the padded row in forward() and cumsum(mask)-1 in generate()). */
+int br_qk_rope(void* qkv, int64_t ld, int M, int n_q_heads, int n_k_heads, int head_dim, const void* q_norm_w,
+               const void* k_norm_w, const int32_t* positions, float theta, float eps, float q_scale, int mode, void* stream);
+/* out[m] = table[ids[m]] (zeros if keep && !keep[m], or id out of range); ids int64 */
+int br_embed_gather(const int64_t* ids, const void* table, int64_t ldt, int64_t vocab, void* out, int64_t ldo, int M, int d,
+                    const int32_t* keep, void* stream);
+int br_scatter_rows(const void* src, int64_t lds, const int32_t* row_map, void* dst, int64_t ldd, int M, int d, void* stream);
+int br_gather_rows(const void* src, int64_t lds, const int32_t* idx, void* dst, int64_t ldd, int M, int d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Attention (replaces the SDPA call under Qwen3Attention / EsmSelfAttention)
+ * q/k/v/o bf16 token-major [B*L, ld] with head h at column h*head_dim; row b attends keys in
+ * [kv_start[b], kv_end[b]) (NULL = whole row) and, if causal, j <= i.  lse [B, Hq, L] f32 optional.
+ * ------------------------------------------------------------------------------------------- */
+int br_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                float* lse, int B, int L, int n_q_heads, int n_kv_heads, int head_dim, const int32_t* kv_start,
+                const int32_t* kv_end, float scale, int causal, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

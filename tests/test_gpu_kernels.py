@@ -146,3 +146,120 @@ def test_lmhead_logprob_and_dlogits(ops, M, V, K):
     onehot = torch.zeros_like(logits); rows = torch.nonzero(tgt >= 0)[:, 0].cuda(); onehot[rows, tgt.cuda()[rows]] = 1
     ref_d = gs[:, None] * (onehot - torch.softmax(logits, -1))
     torch.testing.assert_close(d, ref_d, rtol=2e-2, atol=2e-3)
+
+
+# ---------------------------------------------------------------- row kernels
+@pytest.mark.parametrize("M,d", [(5, 128), (300, 1024), (1000, 2560), (64, 2048), (17, 9728)])
+def test_rmsnorm(ops, M, d):
+    torch.manual_seed(d)
+    x = (torch.randn(M, d) * 3).bfloat16(); w = (1 + 0.1 * torch.randn(d)).bfloat16()
+    y, rstd = ops.rmsnorm(x.cuda(), w.cuda(), 1e-6, want_rstd=True)
+    xf = x.float()
+    r = torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)
+    ref = (w.float() * (xf * r).bfloat16().float()).bfloat16()                 # HF Qwen3RMSNorm rounding points
+    torch.testing.assert_close(rstd.cpu(), r[:, 0], rtol=1e-5, atol=1e-6)
+    diff = (y.cpu().float() - ref.float()).abs()
+    assert (diff > 0).float().mean() < 0.01 and diff.max() <= 0.0625 * ref.float().abs().max()   # rare 1-ulp flips only
+
+
+@pytest.mark.parametrize("M,d", [(7, 128), (1336, 1024), (33, 256)])
+def test_layernorm(ops, M, d):
+    torch.manual_seed(d + 1)
+    x = (torch.randn(M, d) * 2 + 0.3).bfloat16(); w = (1 + 0.1 * torch.randn(d)).bfloat16(); b = (0.1 * torch.randn(d)).bfloat16()
+    y = ops.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-12).cpu().float()
+    ref = torch.nn.functional.layer_norm(x.float(), (d,), w.float(), b.float(), 1e-12)
+    torch.testing.assert_close(y, ref, rtol=1e-2, atol=1e-2)
+
+
+def _hf_rope(x, pos, theta, D):
+    inv = 1.0 / (theta ** (torch.arange(0, D, 2).float() / D))
+    fr = pos.float()[:, None] * inv[None]
+    emb = torch.cat([fr, fr], -1)
+    return emb.cos(), emb.sin()
+
+
+def _rot_half(x):
+    x1, x2 = x[..., : x.shape[-1] // 2], x[..., x.shape[-1] // 2:]
+    return torch.cat([-x2, x1], -1)
+
+
+def test_qk_rope_qwen(ops):
+    torch.manual_seed(9)
+    M, nq, nk, D = 50, 4, 2, 128
+    qkv = torch.randn(M, (nq + 2 * nk) * D).bfloat16()
+    qw = (1 + 0.1 * torch.randn(D)).bfloat16(); kw = (1 + 0.1 * torch.randn(D)).bfloat16()
+    pos = torch.randint(0, 3000, (M,), dtype=torch.int32)
+    out = ops.qk_rope_(qkv.clone().cuda(), nq, nk, D, pos.cuda(), 1e6, q_norm_w=qw.cuda(), k_norm_w=kw.cuda(), eps=1e-6).cpu()
+    cos, sin = _hf_rope(None, pos, 1e6, D); cos, sin = cos.bfloat16(), sin.bfloat16()
+    x = qkv[:, : (nq + nk) * D].view(M, nq + nk, D)
+    w = torch.cat([qw[None].expand(nq, D), kw[None].expand(nk, D)])[None]
+    xf = x.float()
+    xn = (w.float() * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)).bfloat16().float()).bfloat16()
+    ref = (xn * cos[:, None]) + (_rot_half(xn) * sin[:, None])               # bf16 arithmetic as HF does it
+    torch.testing.assert_close(out[:, : (nq + nk) * D].view(M, nq + nk, D).float(), ref.float(), rtol=2e-2, atol=3e-2)
+    assert torch.equal(out[:, (nq + nk) * D:], qkv[:, (nq + nk) * D:])       # V untouched
+
+
+def test_qk_rope_esm(ops):
+    torch.manual_seed(10)
+    M, nh, D = 40, 4, 64
+    qkv = torch.randn(M, 3 * nh * D).bfloat16()
+    pos = torch.arange(M, dtype=torch.int32)
+    out = ops.qk_rope_(qkv.clone().cuda(), nh, nh, D, pos.cuda(), 1e4, q_scale=D ** -0.5, mode=1).cpu()
+    cos, sin = _hf_rope(None, pos, 1e4, D)
+    x = qkv[:, : 2 * nh * D].view(M, 2 * nh, D).clone()
+    x[:, :nh] = x[:, :nh] * D ** -0.5                                          # bf16 multiply, esm/modeling_esm.py:341
+    ref = (x.float() * cos[:, None] + _rot_half(x.float()) * sin[:, None]).bfloat16()
+    torch.testing.assert_close(out[:, : 2 * nh * D].view(M, 2 * nh, D).float(), ref.float(), rtol=1e-2, atol=1e-2)
+
+
+def test_gather_scatter(ops):
+    torch.manual_seed(11)
+    table = torch.randn(100, 256).bfloat16().cuda()
+    ids = torch.randint(0, 100, (3, 17)).cuda()
+    keep = (torch.rand(3, 17) > 0.3).int().cuda()
+    out = ops.embed_gather(ids, table, keep=keep)
+    ref = table[ids.reshape(-1)] * keep.reshape(-1, 1).to(table.dtype)
+    assert torch.equal(out, ref)
+    rm = torch.tensor([5, -1, 0, 9], dtype=torch.int32).cuda()
+    dst = torch.zeros(10, 256, dtype=torch.bfloat16, device="cuda")
+    ops.scatter_rows_(dst, table[:4], rm)
+    assert torch.equal(dst[5], table[0]) and torch.equal(dst[0], table[2]) and torch.equal(dst[9], table[3]) and dst[1].abs().sum() == 0
+    idx = torch.tensor([3, 3, 99], dtype=torch.int32).cuda()
+    assert torch.equal(ops.gather_rows(table, idx), table[idx.long()])
+
+
+# ---------------------------------------------------------------- attention
+def _ref_attn(q, k, v, B, L, nq, nkv, D, ks, ke, scale, causal):
+    qf = q.float().view(B, L, nq, D).transpose(1, 2); kf = k.float().view(B, L, nkv, D).transpose(1, 2)
+    vf = v.float().view(B, L, nkv, D).transpose(1, 2)
+    rep = nq // nkv
+    kf = kf.repeat_interleave(rep, 1); vf = vf.repeat_interleave(rep, 1)
+    s = qf @ kf.transpose(-1, -2) * scale
+    j = torch.arange(L, device=q.device)
+    ok = (j[None, None, None, :] >= ks[:, None, None, None]) & (j[None, None, None, :] < ke[:, None, None, None])
+    if causal:
+        ok = ok & (j[None, None, None, :] <= j[None, None, :, None])
+    s = s.masked_fill(~ok, float("-inf"))
+    lse = torch.logsumexp(s, -1)
+    p = torch.softmax(s, -1).nan_to_num(0.0)
+    o = (p @ vf).transpose(1, 2).reshape(B * L, nq * D)
+    return o, lse
+
+
+@pytest.mark.parametrize("B,L,nq,nkv,D,causal", [(2, 200, 4, 2, 128, True), (3, 77, 8, 2, 128, True), (2, 168, 4, 4, 64, False),
+                                                 (1, 1337, 32, 8, 128, True), (4, 668, 16, 16, 64, False)])
+def test_attn_fwd(ops, B, L, nq, nkv, D, causal):
+    torch.manual_seed(L)
+    W = (nq + 2 * nkv) * D
+    qkv = torch.randn(B * L, W).bfloat16().cuda()
+    q, k, v = qkv[:, : nq * D], qkv[:, nq * D: (nq + nkv) * D], qkv[:, (nq + nkv) * D:]
+    ks = torch.randint(0, L // 3, (B,), dtype=torch.int32).cuda(); ke = torch.randint(2 * L // 3, L + 1, (B,), dtype=torch.int32).cuda()
+    ks[0] = 0; ke[0] = L
+    o, lse = ops.attn_fwd(q, k, v, B, L, nq, nkv, D, kv_start=ks, kv_end=ke, causal=causal, want_lse=True)
+    ro, rlse = _ref_attn(q, k, v, B, L, nq, nkv, D, ks.long(), ke.long(), D ** -0.5, causal)
+    torch.testing.assert_close(o.float(), ro, rtol=2e-2, atol=2e-2)
+    fin = torch.isfinite(rlse)
+    torch.testing.assert_close(lse[fin], rlse[fin], rtol=1e-3, atol=2e-3)
+    assert torch.all(torch.isinf(lse[~fin]))
+    assert o.float()[(~fin).transpose(1, 2).reshape(B * L, nq).repeat_interleave(D, 1)].abs().max().item() == 0 if (~fin).any() else True
