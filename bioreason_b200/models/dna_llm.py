@@ -1,0 +1,212 @@
+"""B200-native `DNALLMModel` -- same Python surface as bioreason/models/dna_llm.py:18-305, math in libbioreason_b200.
+
+What is kept from the reference: constructor kwargs, `forward(input_ids, attention_mask, dna_tokenized,
+batch_idx_map, labels=None, **kw)` returning an object with `.logits` / `.loss`, `generate(...)` returning completion-only
+ids, the two ValueErrors, and the attributes callers touch (`text_model`, `dna_model`, `dna_projection`, `text_config`,
+`dna_config`, `dna_token_id`, `max_length_*`, `text_hidden_size`, `dna_hidden_size`).  `text_model` / `dna_model` are the
+HF module trees (state_dict keys, `named_modules()` with nn.Linear leaves, `.config`) whose storage is re-pointed into
+the fused kernel layout (packing.py); their own `forward` is never on the product path.
+
+What differs by design: the encoder's unused MLM head is skipped, the per-sequence `.item()` syncs are gone (one
+combined count check per call), and logits are materialised lazily -- `per_token_logps()` and `.loss` use the fused
+lm_head + log-sum-exp kernel and never write [B, L, V] to HBM.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import engine, ops
+from ..configs import dna_config as _dna_config
+from ..configs import text_config as _text_config
+from ..packing import pack_decoder, pack_encoder
+
+_TEXT_ALIASES = {"Qwen/Qwen3-4B": "qwen3-4b", "Qwen/Qwen3-1.7B": "qwen3-1.7b"}
+_DNA_ALIASES = {"InstaDeepAI/nucleotide-transformer-v2-500m-multi-species": "nt-v2-500m"}
+
+
+class LazyCausalLMOutput:
+    """`.logits` ([B, L, V]) is computed on first access; `.loss` comes from the fused CE kernel."""
+
+    def __init__(self, model, hidden, B, L, loss=None):
+        self._model, self._hidden, self._B, self._L = model, hidden, B, L
+        self.loss = loss
+        self._logits = None
+
+    @property
+    def logits(self):
+        if self._logits is None:
+            W = self._model._dec
+            self._logits = ops.gemm(self._hidden, W.lm_head).view(self._B, self._L, -1)
+        return self._logits
+
+    @property
+    def hidden_states(self):
+        return self._hidden.view(self._B, self._L, -1)
+
+
+class DNALLMModel(nn.Module):
+    def __init__(self, text_model_name, dna_model_name, cache_dir: Optional[str] = None, max_length_dna: int = 2048,
+                 max_length_text: int = 512, text_model_finetune: bool = True, dna_model_finetune: bool = True,
+                 dna_is_evo2: bool = False, dna_embedding_layer: str = None, *, seed: int = 1234, device="cuda", **kwargs):
+        # **kwargs absorbs `debug=False` passed by reason.py:418 (not in the reference signature either)
+        super().__init__()
+        if dna_is_evo2:
+            raise NotImplementedError("Evo2 (StripedHyena-2) encoder is SURVEY.md §8f 'next'; NT-v2 is the path built here")
+        if not torch.cuda.is_available():
+            raise RuntimeError("bioreason_b200.DNALLMModel needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.text_model_finetune, self.dna_model_finetune = text_model_finetune, dna_model_finetune
+        self.max_length_dna, self.max_length_text = max_length_dna, max_length_text
+        self.dna_is_evo2, self.dna_embedding_layer = dna_is_evo2, dna_embedding_layer
+        self.warnings_issued = {}                                           # grpo_trainer.py:411 writes into it
+        text_model, dna_model = self._build_modules(text_model_name, dna_model_name, cache_dir, seed)
+        self.text_model, self.dna_model = text_model, dna_model
+        self.text_config, self.dna_config = text_model.config, dna_model.config
+        self.config = self.text_config                                      # grpo_trainer.py:472 touches model.config
+        self.text_tokenizer = self.dna_tokenizer = self.processor = None    # no tokenizer files offline
+        self.text_hidden_size, self.dna_hidden_size = self.text_config.hidden_size, self.dna_config.hidden_size
+        g = torch.Generator().manual_seed(seed + 7)
+        self.dna_projection = nn.Linear(self.dna_hidden_size, self.text_hidden_size)     # dna_llm.py:97 (fp32 master)
+        with torch.no_grad():
+            bound = self.dna_hidden_size ** -0.5
+            self.dna_projection.weight.copy_((torch.rand(self.dna_projection.weight.shape, generator=g) * 2 - 1) * bound)
+            self.dna_projection.bias.copy_((torch.rand(self.dna_projection.bias.shape, generator=g) * 2 - 1) * bound)
+        self.dna_projection.to(device)
+        ids = getattr(self.text_config, "dna_token_ids", None)
+        self.dna_token_id = ids[1] if ids else None
+        self._dec = pack_decoder(self.text_model, device)
+        self._enc = pack_encoder(self.dna_model, device)
+        self._proj_w16 = self._proj_b16 = None
+        self._lora = None
+        self.sync_projection()
+
+    # ------------------------------------------------------------------ construction helpers
+    @staticmethod
+    def _build_modules(text_name, dna_name, cache_dir, seed):
+        from transformers import EsmForMaskedLM, Qwen3ForCausalLM
+        def resolve(name, aliases, factory):
+            if not isinstance(name, str):
+                return name                                                  # a config object
+            if os.path.isdir(name):
+                return None                                                  # local checkpoint directory
+            key = aliases.get(name, name)
+            return factory(key)
+        tcfg = resolve(text_name, _TEXT_ALIASES, _text_config)
+        dcfg = resolve(dna_name, _DNA_ALIASES, _dna_config)
+        if tcfg is None or dcfg is None:
+            raise NotImplementedError("loading local checkpoints: SURVEY.md §8f rank 4 (checkpoint interop)")
+        # seeded random init at the real shapes (no weights exist offline); built directly on the GPU in bf16
+        dt = torch.get_default_dtype()
+        try:
+            torch.set_default_dtype(torch.bfloat16)
+            with torch.device("cuda"):
+                torch.manual_seed(seed)
+                text = Qwen3ForCausalLM(tcfg)
+                torch.manual_seed(seed + 1)
+                dna = EsmForMaskedLM(dcfg)
+                if getattr(dcfg, "gated_mlp", False):
+                    for layer in dna.esm.encoder.layer:
+                        F, d = dcfg.intermediate_size, dcfg.hidden_size
+                        layer.intermediate.dense = nn.Linear(d, 2 * F, bias=getattr(dcfg, "add_bias_fc", False))
+                        layer.output.dense = nn.Linear(F, d, bias=getattr(dcfg, "add_bias_fc", False))
+                        nn.init.normal_(layer.intermediate.dense.weight, std=0.02)
+                        nn.init.normal_(layer.output.dense.weight, std=0.02)
+        finally:
+            torch.set_default_dtype(dt)
+        return text.eval(), dna.eval()
+
+    @classmethod
+    def from_oracle(cls, oracle_model, device="cuda"):
+        """Test helper: adopt the weights of an oracle/HF-shaped model (same state_dict keys) so both sides compute
+        on identical parameters."""
+        tc, dc = oracle_model.text_config, oracle_model.dna_config
+        self = cls(tc, dc, device=device)
+        self.load_weights({k: v for k, v in oracle_model.state_dict().items()})
+        return self
+
+    def load_weights(self, state_dict: Dict[str, torch.Tensor]):
+        """load_state_dict(strict=False) that tolerates the NT-v2 FFN layout and refreshes kernel-layout copies."""
+        own = self.state_dict()
+        with torch.no_grad():
+            for k, v in state_dict.items():
+                if k in own and own[k].shape == v.shape:
+                    own[k].copy_(v.to(own[k].dtype))
+        # the encoder's interleaved gate/up copy and the projector compute copy are derived -> rebuild
+        F = self.dna_config.intermediate_size
+        with torch.no_grad():
+            for layer, Lw in zip(self.dna_model.esm.encoder.layer, self._enc.layers):
+                w = layer.intermediate.dense.weight.data
+                g3 = Lw.w_gu.view(F, 2, -1)
+                g3[:, 0, :].copy_(w[:F]); g3[:, 1, :].copy_(w[F:])
+        self._dec.w_T_stale = True
+        self.sync_projection()
+
+    def sync_projection(self):
+        """bf16 compute copy of the (fp32 master) projector; call after every optimizer step."""
+        self._proj_w16 = self.dna_projection.weight.detach().to(torch.bfloat16).contiguous()
+        self._proj_b16 = self.dna_projection.bias.detach().to(torch.bfloat16).contiguous()
+
+    # ------------------------------------------------------------------ hot path
+    def merged_embeddings(self, input_ids, dna_tokenized, batch_idx_map, *, return_proj_inputs: bool = False):
+        """dna_llm.py:211-229 + 103-179: text-embedding gather, encoder, projector GEMM whose epilogue scatters rows
+        straight into the <|dna_pad|> slots."""
+        dev = self._dec.embed.device
+        input_ids = input_ids.to(dev)
+        B, L = input_ids.shape
+        emb = ops.embed_gather(input_ids, self._dec.embed)                  # [B*L, d]
+        aux = None
+        if dna_tokenized is not None and batch_idx_map:
+            dna_ids = dna_tokenized["input_ids"].to(dev)
+            dna_mask = dna_tokenized["attention_mask"].to(dev)
+            row_map, n_feat, n_slots = engine.dna_row_map(input_ids, self.dna_token_id, dna_mask, list(batch_idx_map))
+            n_feat, n_slots = torch.stack([n_feat, n_slots]).tolist()       # the one host sync (reference: n_seq + 1)
+            if n_feat != n_slots:
+                raise ValueError(f"DNA features and DNA tokens do not match: features {n_feat}, tokens: {n_slots}")
+            with torch.no_grad():
+                enc = engine.encoder_forward(self._enc, dna_ids, dna_mask)  # [n_seq*S, d_dna], never gets grad
+            ops.gemm(enc, self._proj_w16, bias=self._proj_b16, out=emb, row_map=row_map)
+            aux = (enc, row_map)
+        return (emb, aux) if return_proj_inputs else emb
+
+    def forward(self, input_ids=None, attention_mask=None, dna_tokenized=None, batch_idx_map=None, labels=None, **kwargs):
+        if input_ids is None or attention_mask is None:
+            raise ValueError("Either 'inputs' or 'input_ids'/'attention_mask' must be provided")
+        dev = self._dec.embed.device
+        B, L = input_ids.shape
+        attention_mask = attention_mask.to(dev)
+        emb = self.merged_embeddings(input_ids, dna_tokenized, batch_idx_map)
+        ks, ke = engine.mask_window(attention_mask)
+        pos = engine.forward_positions(B, L, dev)                           # no position_ids -> arange
+        hidden = engine.decoder_forward(self._dec, emb, B, L, pos, ks, ke, lora=self._lora)
+        loss = None
+        if labels is not None:
+            loss = self._ce_loss(hidden, labels.to(dev), B, L)
+        return LazyCausalLMOutput(self, hidden, B, L, loss)
+
+    def _ce_loss(self, hidden, labels, B, L):
+        """HF ForCausalLMLoss (loss/loss_utils.py:28-67): shift, ignore -100, mean -- on the fused lm_head kernel."""
+        tgt = torch.full((B, L), -1, device=labels.device, dtype=torch.int32)
+        tgt[:, :-1] = torch.where(labels[:, 1:] == -100, -1, labels[:, 1:]).to(torch.int32)
+        logp, _ = ops.lmhead_logprob(hidden, self._dec.lm_head, tgt.reshape(-1))
+        n = (tgt >= 0).sum().clamp(min=1)
+        return -(logp.sum() / n)
+
+    def per_token_logps(self, input_ids, attention_mask, dna_tokenized=None, batch_idx_map=None, keep_last: Optional[int] = None):
+        """Fused equivalent of `_get_per_token_logps` (grpo_trainer.py:510-520): [B, L-1] (or the last `keep_last`
+        columns, i.e. the `[:, P-1:]` slice the trainer takes) log-probs of the realised next tokens; no [B, L, V]."""
+        out = self.forward(input_ids, attention_mask, dna_tokenized, batch_idx_map)
+        return self.logps_from_hidden(out._hidden, input_ids, keep_last)
+
+    def logps_from_hidden(self, hidden, input_ids, keep_last=None):
+        dev = hidden.device
+        B, L = input_ids.shape
+        n = L - 1 if keep_last is None else keep_last
+        cols = torch.arange(L - 1 - n, L - 1, device=dev)
+        rows = (torch.arange(B, device=dev)[:, None] * L + cols[None, :]).reshape(-1).to(torch.int32)
+        h_sel = ops.gather_rows(hidden, rows)
+        tgt = input_ids.to(dev)[:, L - n:].reshape(-1)
+        logp, _ = ops.lmhead_logprob(h_sel, self._dec.lm_head, tgt)
+        return logp.view(B, n)

@@ -1,0 +1,75 @@
+"""End-to-end DNA-LLM forward parity: CUDA path vs the CPU oracle / the golden reference outputs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _to_cuda_batch(b):
+    return b   # DNALLMModel moves tensors itself (as HF/accelerate would)
+
+
+def _err_budget(test_logits, ref32, ref16, valid):
+    """Regime: bf16 storage / fp32 accumulate.  Accept if we sit as close to the reference's fp32 result as the
+    reference's OWN --bf16 path does (x2 slack), measured over attended positions."""
+    e_mine = (test_logits - ref32)[valid].abs()
+    e_ref = (ref16 - ref32)[valid].abs()
+    return e_mine.max().item(), e_ref.max().item(), e_mine.mean().item(), e_ref.mean().item()
+
+
+def test_forward_tiny_golden(golden, tiny_oracle):
+    from bioreason_b200.models import DNALLMModel
+    m = DNALLMModel.from_oracle(tiny_oracle)
+    A = golden["A"]
+    out = m(**A["batch"], labels=A["labels"])
+    logits = out.logits.float().cpu()
+    valid = A["batch"]["attention_mask"].bool()
+    mx, rmx, mean, rmean = _err_budget(logits, A["logits"], A["logits_bf16"], valid)
+    print(f"tiny: max|err| {mx:.4g} (reference bf16 path: {rmx:.4g}); mean {mean:.4g} (ref {rmean:.4g}); logit std {A['logits'][valid].std():.3g}")
+    assert mx <= 2.0 * rmx + 1e-3 and mean <= 2.0 * rmean + 1e-4
+    assert abs(out.loss.item() - A["loss"].item()) <= 2 * abs(A["loss_bf16"].item() - A["loss"].item()) + 2e-3
+    # text-only path
+    Bc = golden["B"]
+    lb = m(**Bc["batch"]).logits.float().cpu()
+    vb = Bc["batch"]["attention_mask"].bool()
+    assert (lb - Bc["logits"])[vb].abs().max().item() <= 2.0 * rmx + 1e-3
+    # count mismatch raises exactly like dna_llm.py:222-225
+    with pytest.raises(ValueError, match="do not match"):
+        m(**golden["C"]["batch"])
+    with pytest.raises(ValueError, match="must be provided"):
+        m(input_ids=None, attention_mask=None)
+
+
+def test_per_token_logps_tiny_golden(golden, tiny_oracle):
+    from bioreason_b200.models import DNALLMModel
+    m = DNALLMModel.from_oracle(tiny_oracle)
+    E, D = golden["E"], golden["D"]
+    lp = m.per_token_logps(E["input_ids"], E["attention_mask"], D["batch"]["dna_tokenized"], D["batch"]["batch_idx_map"]).cpu()
+    att = E["attention_mask"][:, 1:].bool()
+    err = (lp - E["logps"])[att].abs().max().item()
+    print("logps max err", err)
+    assert err < 0.02
+    C = E["completion_ids"].shape[1]
+    lp_c = m.per_token_logps(E["input_ids"], E["attention_mask"], D["batch"]["dna_tokenized"], D["batch"]["batch_idx_map"], keep_last=C).cpu()
+    assert torch.equal(lp_c, lp[:, -C:])
+
+
+@pytest.mark.parametrize("B,n_seq,dna_len,text_len", [(2, 2, [40, 33], [70, 51]), (3, 1, 168, 128)])
+def test_forward_small_vs_oracle(B, n_seq, dna_len, text_len):
+    """Bigger-than-tiny shapes (multi-tile GEMMs, several attention blocks) against the fp32 CPU oracle."""
+    from bioreason_b200.configs import text_config, dna_config
+    from bioreason_b200.models import DNALLMModel
+    from oracle.models import build_oracle, synth_batch
+    tc, dc = text_config("small"), dna_config("small")
+    oracle = build_oracle(tc, dc, seed=7)
+    batch = synth_batch(tc, dc, batch=B, n_seq=n_seq, dna_len=dna_len, text_len=text_len, seed=3)
+    with torch.no_grad():
+        ref32 = oracle(**batch).logits
+        ref16 = oracle.to(torch.bfloat16)(**batch).logits.float()
+    oracle.float()
+    m = DNALLMModel.from_oracle(oracle)
+    logits = m(**batch).logits.float().cpu()
+    valid = batch["attention_mask"].bool()
+    mx, rmx, mean, rmean = _err_budget(logits, ref32, ref16, valid)
+    print(f"small: max|err| {mx:.4g} (HF bf16: {rmx:.4g}); mean {mean:.4g} (HF bf16 {rmean:.4g}); logit std {ref32[valid].std():.3g}")
+    assert mx <= 2.0 * rmx + 1e-3 and mean <= 2.0 * rmean + 1e-4
