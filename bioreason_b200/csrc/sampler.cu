@@ -1,0 +1,211 @@
+// Fused next-token sampler for the rollout: temperature -> top-k -> top-p -> draw, plus EOS / pad bookkeeping, one CTA
+// per row, no host round trip.  Replaces the HF logits warpers + softmax + torch.multinomial / argmax and the
+// unfinished_sequences bookkeeping (HF generation/utils.py:1214-1223, 2762-2797; grpo_trainer.py:384-391).
+//
+// top-k threshold: exact radix select over the order-preserving uint32 image of the fp32 logits (3 histogram passes
+// of 11/11/10 bits, 151 936 logits stay L2-resident), ties at the threshold are all kept like HF's
+// `scores < topk(scores)[..., -1]`.  top-p follows TopPLogitsWarper (ascending cumulative sum, drop while
+// cum <= 1 - p, always keep the best).  The draw is inverse-CDF over the kept tokens in ascending token id with a
+// caller-supplied uniform per (step, row): torch.multinomial's Philox consumption cannot be reproduced outside
+// torch, so parity is defined on supplied uniforms (SURVEY.md §7 "Sampling parity").
+#include "br_common.cuh"
+#include "../../include/bioreason_b200.h"
+
+namespace {
+
+constexpr int MAXC = 1024;
+
+__device__ __forceinline__ uint32_t fkey(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// find bin b (descending scan) such that count(bins > b) < k <= count(bins >= b); returns b and updates k_rem
+__device__ int find_bin(const int* hist, int nbins, int& k_rem, int* s_tmp) {
+    // executed by warp 0; nbins multiple of 32
+    const int lane = threadIdx.x & 31;
+    const int per = nbins / 32;
+    const int hi = nbins - 1 - lane * per;                      // lane 0 owns the top chunk
+    int sum = 0;
+    for (int i = 0; i < per; ++i) sum += hist[hi - i];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    const int excl = incl - sum;
+    const bool mine = (excl < k_rem) && (incl >= k_rem);
+    if (mine) {
+        int acc = excl, b = hi;
+        for (int i = 0; i < per; ++i) {
+            b = hi - i;
+            if (acc + hist[b] >= k_rem) break;
+            acc += hist[b];
+        }
+        s_tmp[0] = b; s_tmp[1] = k_rem - acc;
+    }
+    __syncwarp();
+    int b = s_tmp[0];
+    k_rem = s_tmp[1];
+    return b;
+}
+
+__global__ void __launch_bounds__(1024) sampler_kernel(const float* __restrict__ logits, long long ld, int V, float temperature, int top_k,
+                                                       float top_p, int do_sample, const float* __restrict__ uniforms,
+                                                       const int* __restrict__ step_ptr, int R, int max_steps, long long eos_id,
+                                                       long long pad_id, int* __restrict__ finished, long long* __restrict__ tokens,
+                                                       long long* __restrict__ next_ids) {
+    __shared__ int hist[2048];
+    __shared__ int s_tmp[4];
+    __shared__ float c_val[MAXC];
+    __shared__ int c_idx[MAXC];
+    __shared__ float o_val[MAXC];
+    __shared__ int o_idx[MAXC];
+    __shared__ int s_count;
+    __shared__ float r_val[32];
+    __shared__ int r_idx[32];
+
+    const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* x = logits + (long long)row * ld;
+    const int step = step_ptr ? *step_ptr : 0;
+    long long choice;
+
+    if (!do_sample) {
+        float bv = -INFINITY; int bi = 0x7fffffff;
+        for (int i = tid; i < V; i += blockDim.x) { float v = x[i]; if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; } }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, bv, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { r_val[warp] = bv; r_idx[warp] = bi; }
+        __syncthreads();
+        if (warp == 0) {
+            bv = lane < (blockDim.x >> 5) ? r_val[lane] : -INFINITY; bi = lane < (blockDim.x >> 5) ? r_idx[lane] : 0x7fffffff;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                float ov = __shfl_xor_sync(0xffffffffu, bv, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) s_tmp[2] = bi;
+        }
+        __syncthreads();
+        choice = s_tmp[2];
+    } else {
+        // ---- exact k-th largest key by 3-pass radix select
+        uint32_t prefix = 0; int k_rem = top_k;
+        for (int pass = 0; pass < 3; ++pass) {
+            const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+            const int nb = pass == 2 ? 1024 : 2048;
+            for (int i = tid; i < 2048; i += blockDim.x) hist[i] = 0;
+            __syncthreads();
+            for (int i = tid; i < V; i += blockDim.x) {
+                const uint32_t k = fkey(x[i]);
+                bool in;
+                if (pass == 0) in = true; else if (pass == 1) in = (k >> 21) == prefix; else in = (k >> 10) == prefix;
+                if (in) atomicAdd(&hist[(k >> shift) & (nb - 1)], 1);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                int kr = k_rem;
+                int b = find_bin(hist, nb, kr, s_tmp);
+                if (lane == 0) { s_tmp[2] = b; s_tmp[3] = kr; }
+            }
+            __syncthreads();
+            const int b = s_tmp[2];
+            k_rem = s_tmp[3];
+            prefix = pass == 0 ? (uint32_t)b : (pass == 1 ? ((prefix << 11) | (uint32_t)b) : ((prefix << 10) | (uint32_t)b));
+            __syncthreads();
+        }
+        const uint32_t thr = prefix;
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        for (int i = tid; i < V; i += blockDim.x) {
+            const float v = x[i];
+            if (fkey(v) >= thr) {
+                const int s = atomicAdd(&s_count, 1);
+                if (s < MAXC) { c_val[s] = v; c_idx[s] = i; }
+            }
+        }
+        __syncthreads();
+        const int c = min(s_count, MAXC);
+        // ---- rank sort: descending value, ties by ascending index
+        if (tid < c) {
+            const float v = c_val[tid]; const int id = c_idx[tid];
+            int rank = 0;
+            for (int j = 0; j < c; ++j) rank += (c_val[j] > v) || (c_val[j] == v && c_idx[j] < id);
+            o_val[rank] = v; o_idx[rank] = id;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // softmax over the kept-by-top-k set at temperature T (fp32), descending order
+            const float inv_t = 1.f / temperature;
+            const float mx = o_val[0] * inv_t;
+            float tot = 0.f;
+            for (int j = 0; j < c; ++j) { c_val[j] = __expf(o_val[j] * inv_t - mx); tot += c_val[j]; }
+            // top-p: ascending cumulative sum; drop while cum <= 1 - p; the best token always stays
+            int keep = c;
+            if (top_p < 1.f) {
+                float cum = 0.f;
+                const float lim = 1.f - top_p;
+                for (int j = c - 1; j >= 1; --j) {
+                    cum += c_val[j] / tot;
+                    if (cum <= lim) keep = j; else break;
+                }
+            }
+            float ktot = 0.f;
+            for (int j = 0; j < keep; ++j) ktot += c_val[j];
+            // inverse CDF in ascending token id
+            const float u = uniforms[(long long)step * R + row];
+            const float target = u * ktot;
+            // selection by repeatedly taking the smallest remaining id (keep is ~20)
+            float acc = 0.f; int chosen = o_idx[0]; int last_id = -1;
+            for (int n = 0; n < keep; ++n) {
+                int best = -1;
+                for (int j = 0; j < keep; ++j) if (o_idx[j] > last_id && (best < 0 || o_idx[j] < o_idx[best])) best = j;
+                acc += c_val[best]; last_id = o_idx[best]; chosen = o_idx[best];
+                if (acc > target) break;
+            }
+            s_tmp[2] = chosen;
+        }
+        __syncthreads();
+        choice = s_tmp[2];
+    }
+    if (tid == 0) {
+        const int fin = finished ? finished[row] : 0;
+        long long tok = fin ? pad_id : choice;                         // finished rows emit pad (HF :2796-2797)
+        if (tokens && step < max_steps) tokens[(long long)row * max_steps + step] = tok;
+        if (next_ids) next_ids[row] = tok;
+        if (finished && !fin && eos_id >= 0 && tok == eos_id) finished[row] = 1;
+    }
+}
+
+__global__ void advance_kernel(int* step, int* cur_len, int R) {
+    const int i = threadIdx.x;
+    if (i < R) cur_len[i] += 1;
+    if (i == 0 && step) *step += 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int br_sample_next(const float* logits, int64_t ld, int R, int V, float temperature, int top_k, float top_p, int do_sample,
+                   const float* uniforms, const int32_t* step, int max_steps, int64_t eos_id, int64_t pad_id, int32_t* finished,
+                   int64_t* tokens, int64_t* next_ids, void* stream) {
+    BR_CHECK_ARG(R > 0 && V > 0, "sample_next: empty");
+    if (do_sample) {
+        BR_CHECK_ARG(temperature > 0.f && top_k >= 1 && top_k <= MAXC && top_p > 0.f && uniforms, "sample_next: need T > 0, 1 <= top_k <= %d, top_p > 0 and a uniforms buffer", MAXC);
+    }
+    sampler_kernel<<<R, 1024, 0, (cudaStream_t)stream>>>(logits, ld, V, temperature, top_k, top_p, do_sample, uniforms, step, R, max_steps,
+                                                        (long long)eos_id, (long long)pad_id, finished, (long long*)tokens, (long long*)next_ids);
+    BR_CHECK_LAUNCH();
+    return BR_OK;
+}
+
+int br_decode_advance(int32_t* step, int32_t* cur_len, int R, void* stream) {
+    BR_CHECK_ARG(R > 0 && R <= 1024, "decode_advance: R in [1, 1024]");
+    advance_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(step, cur_len, R);
+    BR_CHECK_LAUNCH();
+    return BR_OK;
+}
+
+}  // extern "C"

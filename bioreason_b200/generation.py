@@ -1,0 +1,256 @@
+"""Rollout engine: prefix-shared prefill + CUDA-graph decode loop on the paged-KV kernels.
+
+Replaces `DNALLMModel.generate` -> `text_model.generate(inputs_embeds=..., use_cache=True, **kw)` (dna_llm.py:246-305; HF
+generation/utils.py:2760-2800).  Semantics kept: completion-only ids; position_ids = cumsum(mask)-1 (pads excluded);
+warper order temperature -> top-k -> top-p; finished rows emit pad; output trimmed to the longest unfinished row.
+Redundancy removed: identical consecutive prompts (the G samples of a GRPO group) are encoded and
+prefilled once and share their prompt KV pages.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import engine, ops
+from .packing import DecoderW
+
+PAGE = 64
+
+
+@dataclass
+class SamplingParams:
+    max_new_tokens: int = 20
+    do_sample: bool = False
+    temperature: float = 1.0
+    top_k: int = 50
+    top_p: float = 1.0
+    eos_token_id: Optional[int] = None
+    pad_token_id: Optional[int] = None
+
+    @classmethod
+    def from_hf_kwargs(cls, model_cfg, kwargs):
+        gc = kwargs.get("generation_config", None)
+        def pick(name, default):
+            if name in kwargs and kwargs[name] is not None:
+                return kwargs[name]
+            if gc is not None and getattr(gc, name, None) is not None:
+                return getattr(gc, name)
+            return default
+        eos = pick("eos_token_id", getattr(model_cfg, "eos_token_id", None))
+        if isinstance(eos, (list, tuple)):
+            eos = eos[0]
+        pad = pick("pad_token_id", getattr(model_cfg, "pad_token_id", None))
+        if pad is None:
+            pad = eos if eos is not None else 0
+        return cls(max_new_tokens=int(pick("max_new_tokens", 20)), do_sample=bool(pick("do_sample", False)),
+                   temperature=float(pick("temperature", 1.0)), top_k=int(pick("top_k", 50) or 0), top_p=float(pick("top_p", 1.0)),
+                   eos_token_id=eos, pad_token_id=pad)
+
+
+def detect_group_size(input_ids: torch.Tensor, dna_tokenized, batch_idx_map) -> torch.Tensor:
+    """eq[i] = row i is identical to row i-1 (text ids and its DNA sequences) -- device tensor, no sync."""
+    B = input_ids.shape[0]
+    eq = torch.zeros(B, dtype=torch.bool, device=input_ids.device)
+    if B > 1:
+        eq[1:] = (input_ids[1:] == input_ids[:-1]).all(dim=1)
+        if dna_tokenized is not None and batch_idx_map:
+            counts = [0] * B
+            for b in batch_idx_map:
+                counts[b] += 1
+            if len(set(counts)) == 1 and list(batch_idx_map) == sorted(batch_idx_map):
+                d = dna_tokenized["input_ids"].to(input_ids.device).view(B, -1)
+                eq[1:] &= (d[1:] == d[:-1]).all(dim=1)
+            else:
+                eq[:] = False
+    return eq
+
+
+def group_size_from_flags(eq: List[bool]) -> int:
+    B = len(eq)
+    for G in range(B, 0, -1):
+        if B % G == 0 and all(eq[i] for i in range(B) if i % G != 0):
+            return G
+    return 1
+
+
+class RolloutEngine:
+    """Owns the KV page pool, decode scratch and the captured decode-step graph for one model."""
+
+    def __init__(self, model):
+        self.model = model
+        self._graph = None
+        self._graph_key = None
+        self._weights = None            # DecoderW used for the rollout (base, or base+LoRA merged)
+
+    # ------------------------------------------------------------------
+    def rollout_weights(self) -> DecoderW:
+        m = self.model
+        return m._rollout_dec if getattr(m, "_rollout_dec", None) is not None else m._dec
+
+    @torch.no_grad()
+    def generate(self, input_ids, attention_mask, dna_tokenized=None, batch_idx_map=None, *, params: SamplingParams,
+                 uniforms: Optional[torch.Tensor] = None, use_graph: bool = True, return_stats: bool = False):
+        m = self.model
+        W = self.rollout_weights()
+        cfg = W.cfg
+        dev = W.embed.device
+        Hq, Hkv, D, d = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim, cfg.hidden_size
+        theta = cfg.rope_parameters["rope_theta"] if hasattr(cfg, "rope_parameters") else cfg.rope_theta
+        eps = cfg.rms_norm_eps
+        input_ids = input_ids.to(dev)
+        attention_mask = attention_mask.to(dev)
+        B, P = input_ids.shape
+        C = params.max_new_tokens
+
+        # ---- one host sync: grouping flags + prompt lengths
+        eq = detect_group_size(input_ids, dna_tokenized, batch_idx_map)
+        lens = attention_mask.sum(dim=1)
+        host = torch.cat([eq.long(), lens]).tolist()
+        G = group_size_from_flags([bool(x) for x in host[:B]])
+        U = B // G
+        plen = [int(x) for x in host[B:]][::G]                           # prompt length of each unique row
+
+        # ---- encode + prefill the unique prompts only
+        uid = torch.arange(0, B, G, device=dev)
+        u_ids, u_mask = input_ids[uid], attention_mask[uid]
+        if dna_tokenized is not None and batch_idx_map:
+            keep = [i for i, b in enumerate(batch_idx_map) if b % G == 0]
+            kt = torch.tensor(keep, device=dev)
+            u_dna = {k: v.to(dev)[kt] for k, v in dna_tokenized.items() if k in ("input_ids", "attention_mask")}
+            u_map = [batch_idx_map[i] // G for i in keep]
+        else:
+            u_dna, u_map = None, []
+        emb = m.merged_embeddings(u_ids, u_dna, u_map)
+        ks, ke = engine.mask_window(u_mask)
+        pos = engine.generate_positions(u_mask)
+
+        # ---- page plan: full prompt pages are shared by the group, the tail page + generated tokens are private
+        n_full = [l // PAGE for l in plen]
+        n_shared = min(n_full) if G > 1 else 0                           # kernel takes one shared-page count for all groups
+        priv_pages = [math.ceil((l - n_shared * PAGE + C) / PAGE) for l in plen]
+        max_pages = n_shared + max(priv_pages)
+        next_page = 0
+        table = torch.zeros(B, max_pages, dtype=torch.int32)
+        prefill_pages = []                                               # per unique prompt: pages holding its prompt tokens (row 0 of the group)
+        for u in range(U):
+            shared = list(range(next_page, next_page + n_shared)); next_page += n_shared
+            for gidx in range(G):
+                r = u * G + gidx
+                mine = list(range(next_page, next_page + priv_pages[u])); next_page += priv_pages[u]
+                table[r, :n_shared] = torch.tensor(shared, dtype=torch.int32) if n_shared else table[r, :0]
+                table[r, n_shared:n_shared + priv_pages[u]] = torch.tensor(mine, dtype=torch.int32)
+            prefill_pages.append(table[u * G, :math.ceil(plen[u] / PAGE)].clone())
+        n_pages = next_page
+        table = table.to(dev)
+        nl = len(W.layers)
+        kc = torch.empty(nl, n_pages, Hkv, PAGE, D, device=dev, dtype=torch.bfloat16)
+        vc = torch.empty_like(kc)
+        pp_dev = [p.to(dev) for p in prefill_pages]
+
+        def kv_sink(li, qkv):
+            for u in range(U):
+                first = u * P + (P - plen[u])                             # first real token of the left-padded row
+                ops.kv_write_pages(qkv[first:], plen[u], Hq, Hkv, D, pp_dev[u], kc[li], vc[li])
+
+        hidden = engine.decoder_forward(W, emb, U, P, pos, ks, ke, kv_sink=kv_sink)
+        # replicate each group's partially filled tail page to the other G-1 rows
+        if G > 1:
+            src, dst = [], []
+            for u in range(U):
+                n_tail = math.ceil(plen[u] / PAGE) - n_shared
+                for j in range(n_tail):
+                    for gidx in range(1, G):
+                        src.append(int(prefill_pages[u][n_shared + j])); dst.append(int(table[u * G + gidx, n_shared + j]))
+            if src:
+                s_t, d_t = torch.tensor(src, device=dev), torch.tensor(dst, device=dev)
+                kc[:, d_t] = kc[:, s_t]; vc[:, d_t] = vc[:, s_t]
+
+        # ---- decode state
+        R = B
+        tokens = torch.full((R, C), params.pad_token_id if params.pad_token_id is not None else 0, device=dev, dtype=torch.int64)
+        next_ids = torch.zeros(R, device=dev, dtype=torch.int64)
+        finished = torch.zeros(R, device=dev, dtype=torch.int32)
+        step = torch.zeros(1, device=dev, dtype=torch.int32)
+        cur_len = torch.tensor([plen[r // G] for r in range(R)], device=dev, dtype=torch.int32)
+        if params.do_sample:
+            if uniforms is None:
+                uniforms = torch.rand(C, R, device=dev, dtype=torch.float32)
+            uniforms = uniforms.to(dev).float().contiguous()
+            assert uniforms.shape == (C, R)
+        eos = params.eos_token_id if params.eos_token_id is not None else -1
+        scratch = ops.skinny_scratch(max(cfg.vocab_size, 2 * cfg.intermediate_size), dev)
+        splits_shared = min(8, n_shared) if n_shared > 0 else 0
+        splits_private = 2 if n_shared > 0 else 8
+        n_slots = splits_shared + splits_private
+        ws = ops.decode_attn_workspace(R, Hq, D, n_slots, dev)
+        attn_out = torch.empty(R, Hq * D, device=dev, dtype=torch.bfloat16)
+        h = torch.empty(R, d, device=dev, dtype=torch.bfloat16)
+
+        def sample(logits):
+            ops.sample_next(logits, temperature=params.temperature, top_k=params.top_k, top_p=params.top_p, do_sample=params.do_sample,
+                            uniforms=uniforms if params.do_sample else None, step=step, max_steps=C, eos_id=eos,
+                            pad_id=params.pad_token_id if params.pad_token_id is not None else 0, finished=finished, tokens=tokens,
+                            next_ids=next_ids)
+
+        # ---- first token from the prefill's last position (row u replicated G times)
+        last_rows = torch.tensor([u * P + P - 1 for u in range(U) for _ in range(G)], device=dev, dtype=torch.int32)
+        h_last = ops.gather_rows(hidden, last_rows)
+        logits = ops.skinny_gemm(h_last, W.lm_head, scratch, mode=3)
+        sample(logits)
+        step += 1                                                         # cur_len stays: the first generated token sits at index plen
+
+        def decode_step():
+            ops.embed_gather(next_ids, W.embed, out=h)
+            x = h
+            for li, Lw in enumerate(W.layers):
+                xn = ops.rmsnorm(x, Lw.ln1, eps)
+                qkv = ops.skinny_gemm(xn, Lw.w_qkv, scratch)
+                ops.decode_rope_append(qkv, Hq, Hkv, D, Lw.q_norm, Lw.k_norm, cur_len, table, kc[li], vc[li], theta, eps)
+                ops.decode_attn(qkv, kc[li], vc[li], table, cur_len, G, Hq, Hkv, D, n_shared, splits_shared, splits_private, ws, attn_out)
+                x2 = ops.skinny_gemm(attn_out, Lw.w_o, scratch, mode=1, residual=x)
+                xn2 = ops.rmsnorm(x2, Lw.ln2, eps)
+                act = ops.skinny_gemm(xn2, Lw.w_gu, scratch, mode=2)
+                x = ops.skinny_gemm(act, Lw.w_down, scratch, mode=1, residual=x2)
+            xf = ops.rmsnorm(x, W.final_norm, eps)
+            lg = ops.skinny_gemm(xf, W.lm_head, scratch, mode=3)
+            sample(lg)
+            ops.decode_advance(step, cur_len)
+
+        n_steps = C - 1
+        graph = None
+        if use_graph and n_steps > 2:
+            # warm up once on a side stream (allocator + lazy func attributes), then capture one decode step
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            state = [t.clone() for t in (tokens, next_ids, finished, step, cur_len)]
+            with torch.cuda.stream(s):
+                decode_step()
+            torch.cuda.current_stream().wait_stream(s)
+            for t, v in zip((tokens, next_ids, finished, step, cur_len), state):
+                t.copy_(v)                                                # the warm-up step is replayed for real below
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                decode_step()
+            for t, v in zip((tokens, next_ids, finished, step, cur_len), state):
+                t.copy_(v)
+        done_steps = 0
+        check_every = 16
+        while done_steps < n_steps:
+            chunk = min(check_every, n_steps - done_steps) if eos >= 0 else n_steps - done_steps
+            for _ in range(chunk):
+                graph.replay() if graph is not None else decode_step()
+            done_steps += chunk
+            if eos >= 0 and done_steps < n_steps and bool(finished.min().item() == 1):
+                break
+        out = tokens
+        if eos >= 0:
+            # HF stops as soon as every row has finished: trim to the longest row (eos position inclusive)
+            is_eos = out == eos
+            first = torch.where(is_eos.any(1), is_eos.int().argmax(1) + 1, torch.full((R,), min(done_steps + 1, C), device=dev))
+            out = out[:, : int(first.max().item())]
+        if return_stats:
+            return out, dict(G=G, unique_prompts=U, n_shared_pages=n_shared, pages=n_pages, graph=graph is not None)
+        return out

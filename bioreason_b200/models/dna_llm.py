@@ -200,6 +200,23 @@ class DNALLMModel(nn.Module):
         out = self.forward(input_ids, attention_mask, dna_tokenized, batch_idx_map)
         return self.logps_from_hidden(out._hidden, input_ids, keep_last)
 
+    @torch.no_grad()
+    def generate(self, input_ids=None, attention_mask=None, dna_tokenized=None, batch_idx_map=None, **generation_kwargs):
+        """dna_llm.py:246-305: completion-only ids.  Accepts loose kwargs (max_new_tokens, temperature, top_p, top_k,
+        do_sample; train_dna_qwen.py:279-289) and `generation_config=` (grpo_trainer.py:581-584).  Extra: `uniforms=`
+        [max_new_tokens, B] for replayable sampling."""
+        if input_ids is None or attention_mask is None:
+            raise ValueError("Either 'inputs' or 'input_ids'/'attention_mask' must be provided")
+        from ..generation import RolloutEngine, SamplingParams
+        if getattr(self, "_rollout", None) is None:
+            self._rollout = RolloutEngine(self)
+        uniforms = generation_kwargs.pop("uniforms", None)
+        use_graph = generation_kwargs.pop("use_graph", True)
+        return_stats = generation_kwargs.pop("return_stats", False)
+        params = SamplingParams.from_hf_kwargs(self.text_config, generation_kwargs)
+        return self._rollout.generate(input_ids, attention_mask, dna_tokenized, batch_idx_map, params=params, uniforms=uniforms,
+                                      use_graph=use_graph, return_stats=return_stats)
+
     def logps_from_hidden(self, hidden, input_ids, keep_last=None):
         dev = hidden.device
         B, L = input_ids.shape

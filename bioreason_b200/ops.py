@@ -228,3 +228,64 @@ def attn_fwd(q, k, v, B, L, n_q, n_kv, head_dim, *, kv_start=None, kv_end=None, 
                             ptr(lse, "float*"), B, L, n_q, n_kv, head_dim, ptr(kv_start, "int32_t*"), ptr(kv_end, "int32_t*"),
                             float(scale), 1 if causal else 0, _stream()), "attn_fwd")
     return (out, lse) if want_lse else out
+
+
+# ------------------------------------------------------------------ decode
+def skinny_scratch(max_n: int, device) -> torch.Tensor:
+    return torch.zeros(lib().br_skinny_scratch_bytes(max_n), device=device, dtype=torch.uint8)
+
+
+def skinny_gemm(x, w, scratch, *, mode=0, residual=None, out=None):
+    """out[R, N] = x[R, K] @ w[N, K].T for R <= 32 decode rows."""
+    _need_cuda(x, w)
+    R, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        if mode == 3:
+            out = torch.empty(R, N, device=x.device, dtype=torch.float32)
+        else:
+            out = torch.empty(R, N // 2 if mode == 2 else N, device=x.device, dtype=torch.bfloat16)
+    check(lib().br_skinny_gemm(ptr(x), _row_major_2d(x), ptr(w), _row_major_2d(w), ptr(out), _row_major_2d(out), R, N, K, mode,
+                               ptr(residual), _row_major_2d(residual) if residual is not None else 0, ptr(scratch), _stream()),
+          "skinny_gemm")
+    return out
+
+
+def decode_rope_append(qkv, n_q, n_kv, head_dim, q_norm_w, k_norm_w, cur_len, page_table, kcache, vcache, theta, eps):
+    check(lib().br_decode_rope_append(ptr(qkv), _row_major_2d(qkv), qkv.shape[0], n_q, n_kv, head_dim, ptr(q_norm_w), ptr(k_norm_w),
+                                      ptr(cur_len, "int32_t*"), ptr(page_table, "int32_t*"), page_table.shape[1], ptr(kcache),
+                                      ptr(vcache), float(theta), float(eps), _stream()), "decode_rope_append")
+
+
+def kv_write_pages(qkv_from_first_token, n_tok, n_q, n_kv, head_dim, pages, kcache, vcache):
+    check(lib().br_kv_write_pages(ptr(qkv_from_first_token), _row_major_2d(qkv_from_first_token), n_tok, n_q, n_kv, head_dim,
+                                  ptr(pages, "int32_t*"), ptr(kcache), ptr(vcache), _stream()), "kv_write_pages")
+
+
+def decode_attn_workspace(R, n_q, head_dim, n_slots, device):
+    return torch.empty(lib().br_decode_attn_workspace_bytes(R, n_q, head_dim, n_slots), device=device, dtype=torch.uint8)
+
+
+def decode_attn(qkv, kcache, vcache, page_table, cur_len, G, n_q, n_kv, head_dim, n_shared_pages, splits_shared, splits_private,
+                workspace, out, scale=None):
+    R = qkv.shape[0]
+    if scale is None:
+        scale = head_dim ** -0.5
+    check(lib().br_decode_attn(ptr(qkv), _row_major_2d(qkv), ptr(kcache), ptr(vcache), ptr(page_table, "int32_t*"), page_table.shape[1],
+                               ptr(cur_len, "int32_t*"), R, G, n_q, n_kv, head_dim, n_shared_pages, splits_shared, splits_private,
+                               float(scale), ptr(workspace), ptr(out), _row_major_2d(out), _stream()), "decode_attn")
+    return out
+
+
+def sample_next(logits, *, temperature=1.0, top_k=20, top_p=1.0, do_sample=True, uniforms=None, step=None, max_steps=1,
+                eos_id=-1, pad_id=0, finished=None, tokens=None, next_ids=None):
+    R, V = logits.shape
+    assert logits.dtype == torch.float32
+    check(lib().br_sample_next(ptr(logits, "float*"), _row_major_2d(logits), R, V, float(temperature), int(top_k), float(top_p),
+                               1 if do_sample else 0, ptr(uniforms, "float*"), ptr(step, "int32_t*"), int(max_steps), int(eos_id),
+                               int(pad_id), ptr(finished, "int32_t*"), ptr(tokens, "int64_t*"), ptr(next_ids, "int64_t*"), _stream()),
+          "sample_next")
+
+
+def decode_advance(step, cur_len):
+    check(lib().br_decode_advance(ptr(step, "int32_t*"), ptr(cur_len, "int32_t*"), cur_len.numel(), _stream()), "decode_advance")

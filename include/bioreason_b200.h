@@ -110,6 +110,37 @@ int br_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
                 float* lse, int B, int L, int n_q_heads, int n_kv_heads, int head_dim, const int32_t* kv_start,
                 const int32_t* kv_end, float scale, int causal, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Rollout / decode (replaces the HF generate() token loop, DynamicCache and logits warpers reached from
+ * dna_llm.py:298-304; HF generation/utils.py:2760-2800, 1214-1223)
+ * KV cache per layer: K and V are [n_pages, Hkv, 64, head_dim] bf16; page_table int32 [R, max_pages];
+ * cur_len int32 [R] = tokens already cached for the row (the position of the token being decoded).
+ * ------------------------------------------------------------------------------------------- */
+int64_t br_skinny_scratch_bytes(int max_N);
+/* out[R, N] = X[R, K] . W[N, K]^T for R <= 32 (HBM-bound weight streaming). mode 0: bf16; 1: bf16(out) + residual;
+ * 2: SwiGLU over interleaved (gate, up) rows -> [R, N/2]; 3: fp32.  scratch: zero-initialised once, self-cleaning. */
+int br_skinny_gemm(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
+                   const void* residual, int64_t ldr, void* scratch, void* stream);
+/* per-head q/k RMSNorm + RoPE at position cur_len[r]; K and V of the new token go into the row's page, Q stays in qkv */
+int br_decode_rope_append(void* qkv, int64_t ld, int R, int n_q_heads, int n_kv_heads, int head_dim, const void* q_norm_w,
+                          const void* k_norm_w, const int32_t* cur_len, const int32_t* page_table, int max_pages,
+                          void* kcache, void* vcache, float theta, float eps, void* stream);
+/* prefill: copy roped K / V of tokens [0, n_tok) of one prompt row (qkv points at its first real token) into pages[] */
+int br_kv_write_pages(const void* qkv, int64_t ld, int n_tok, int n_q_heads, int n_kv_heads, int head_dim, const int32_t* pages,
+                      void* kcache, void* vcache, void* stream);
+int64_t br_decode_attn_workspace_bytes(int R, int n_q_heads, int head_dim, int n_slots);
+/* one decode-attention step; rows are R/G groups whose first n_shared_pages table entries are identical (prefix sharing:
+ * the shared pass reads each prompt K/V tile once per group). n_slots = splits_shared (if used) + splits_private. */
+int br_decode_attn(const void* qkv, int64_t ld, const void* kcache, const void* vcache, const int32_t* page_table, int max_pages,
+                   const int32_t* cur_len, int R, int G, int n_q_heads, int n_kv_heads, int head_dim, int n_shared_pages,
+                   int splits_shared, int splits_private, float scale, void* workspace, void* out, int64_t ldo, void* stream);
+/* temperature -> top-k -> top-p -> inverse-CDF draw with uniforms[step*R + r] (or argmax when !do_sample); finished rows
+ * emit pad_id; writes tokens[r, step] (int64 [R, max_steps]) and next_ids[r]; eos_id < 0 disables EOS. */
+int br_sample_next(const float* logits, int64_t ld, int R, int V, float temperature, int top_k, float top_p, int do_sample,
+                   const float* uniforms, const int32_t* step, int max_steps, int64_t eos_id, int64_t pad_id, int32_t* finished,
+                   int64_t* tokens, int64_t* next_ids, void* stream);
+int br_decode_advance(int32_t* step, int32_t* cur_len, int R, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,3 +110,19 @@ def test_grpo_loss_torch_and_c(golden, case, beta, lo, hi, use_old):
 def test_repeat_sampler(golden):
     for (n, mini, bs, rep, seed), want in golden["H"].items():
         assert og.repeat_random_sampler(n, mini, bs, rep, seed) == want
+
+
+def test_manual_generate_matches_hf_greedy(golden, tiny_oracle):
+    """Pins oracle/generate.py (the replayable-sampling loop) against HF generate() and the reference's golden ids."""
+    from oracle.generate import manual_generate
+    D = golden["D"]; cfg = tiny_oracle.text_config
+    ids = manual_generate(tiny_oracle, D["batch"], max_new_tokens=12, eos_token_id=cfg.eos_token_id, pad_token_id=cfg.pad_token_id)
+    assert torch.equal(ids, D["greedy"])
+    ids = manual_generate(tiny_oracle, D["ragged_batch"], max_new_tokens=8, eos_token_id=cfg.eos_token_id, pad_token_id=cfg.pad_token_id)
+    assert torch.equal(ids, D["ragged_greedy"])
+    # sampled: every drawn token must be inside HF's own top-k/top-p support and be reproducible from the uniforms
+    u = torch.rand(6, 4, generator=torch.Generator().manual_seed(3))
+    a = manual_generate(tiny_oracle, D["batch"], max_new_tokens=6, do_sample=True, temperature=0.6, top_k=20, top_p=0.95, uniforms=u)
+    b = manual_generate(tiny_oracle, D["batch"], max_new_tokens=6, do_sample=True, temperature=0.6, top_k=20, top_p=0.95, uniforms=u)
+    assert torch.equal(a, b) and a.shape == (4, 6)
+    assert len({tuple(r.tolist()) for r in a}) > 1          # different uniforms per row -> the G samples differ
