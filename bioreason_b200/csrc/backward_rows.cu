@@ -1,0 +1,298 @@
+// Row / elementwise kernels of the hand-written decoder backward: RMSNorm backward (+ residual
+// gradient add), SwiGLU backward on the blocked gate/up layout, q/k-norm + RoPE backward, the LoRA "X^T Y" gradient
+// reduction, bf16 transpose and column sums (projector gradients).  Base weights are frozen (LoRA), so no weight
+// gradients exist for the norms or the base linears.
+#include "br_common.cuh"
+#include "../../include/bioreason_b200.h"
+#include "attn_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+// dx = rstd * (w o dy) - x * rstd^3 * mean(x o w o dy)  (+ dres)
+template <int VEC_ITERS>
+__global__ void rmsnorm_bwd_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ w, const float* __restrict__ rstd,
+                                   const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ dres, long long lddr,
+                                   bf16* __restrict__ dx, long long lddx, int M, int d) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const int nvec = d >> 3;
+    const uint4* xp = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
+    const uint4* gp = reinterpret_cast<const uint4*>(dy + (long long)row * lddy);
+    const uint4* wp = reinterpret_cast<const uint4*>(w);
+    float xv[VEC_ITERS][8], dn[VEC_ITERS][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC_ITERS; ++i) {
+        const int idx = lane + i * 32;
+        if (idx < nvec) {
+            const uint4 a = xp[idx], g = gp[idx], ww = __ldg(wp + idx);
+            const uint32_t as[4] = {a.x, a.y, a.z, a.w}, gs[4] = {g.x, g.y, g.z, g.w}, ws[4] = {ww.x, ww.y, ww.z, ww.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 xf = br::unpack_bf16(as[j]), gf = br::unpack_bf16(gs[j]), wf = br::unpack_bf16(ws[j]);
+                xv[i][2 * j] = xf.x; xv[i][2 * j + 1] = xf.y;
+                dn[i][2 * j] = gf.x * wf.x; dn[i][2 * j + 1] = gf.y * wf.y;
+                dot += xf.x * dn[i][2 * j] + xf.y * dn[i][2 * j + 1];
+            }
+        }
+    }
+    dot = br::warp_sum(dot);
+    const float r = rstd[row];
+    const float c = dot * r * r * r / (float)d;
+    const uint4* rp = dres ? reinterpret_cast<const uint4*>(dres + (long long)row * lddr) : nullptr;
+    uint4* op = reinterpret_cast<uint4*>(dx + (long long)row * lddx);
+#pragma unroll
+    for (int i = 0; i < VEC_ITERS; ++i) {
+        const int idx = lane + i * 32;
+        if (idx < nvec) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = r * dn[i][j] - xv[i][j] * c;
+            if (rp) {
+                const uint4 rr = rp[idx];
+                const uint32_t rs[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float2 f = br::unpack_bf16(rs[j]); o[2 * j] += f.x; o[2 * j + 1] += f.y; }
+            }
+            op[idx] = make_uint4(br::pack_bf16(o[0], o[1]), br::pack_bf16(o[2], o[3]), br::pack_bf16(o[4], o[5]), br::pack_bf16(o[6], o[7]));
+        }
+    }
+}
+
+// gu / dgu: blocks of 16 columns = 8 gate | 8 up;  dact [M, F]
+__global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, long long ldgu, const bf16* __restrict__ dact, long long ldda,
+                                  bf16* __restrict__ dgu, long long lddgu, long long M, int F) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // one thread per 8 outputs
+    const int per_row = F >> 3;
+    if (i >= M * per_row) return;
+    const long long m = i / per_row; const int blk = (int)(i % per_row);
+    const uint4 gv = *reinterpret_cast<const uint4*>(gu + m * ldgu + blk * 16);
+    const uint4 uv = *reinterpret_cast<const uint4*>(gu + m * ldgu + blk * 16 + 8);
+    const uint4 dv = *reinterpret_cast<const uint4*>(dact + m * ldda + blk * 8);
+    const uint32_t gs[4] = {gv.x, gv.y, gv.z, gv.w}, us[4] = {uv.x, uv.y, uv.z, uv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
+    uint32_t og[4], ou[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 g = br::unpack_bf16(gs[j]), u = br::unpack_bf16(us[j]), d = br::unpack_bf16(ds[j]);
+        const float s0 = 1.f / (1.f + __expf(-g.x)), s1 = 1.f / (1.f + __expf(-g.y));
+        og[j] = br::pack_bf16(d.x * u.x * s0 * (1.f + g.x * (1.f - s0)), d.y * u.y * s1 * (1.f + g.y * (1.f - s1)));
+        ou[j] = br::pack_bf16(d.x * g.x * s0, d.y * g.y * s1);
+    }
+    *reinterpret_cast<uint4*>(dgu + m * lddgu + blk * 16) = make_uint4(og[0], og[1], og[2], og[3]);
+    *reinterpret_cast<uint4*>(dgu + m * lddgu + blk * 16 + 8) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+}
+
+// in place on dqkv (q and k heads): inverse rotation, then the per-head RMSNorm backward using the saved pre-norm values
+template <int D>
+__global__ void qk_rope_bwd_kernel(bf16* __restrict__ dqkv, long long ldd, const bf16* __restrict__ pre, long long ldp, int M, int n_q, int n_k,
+                                   const bf16* __restrict__ qw, const bf16* __restrict__ kw, const int* __restrict__ pos, float theta, float eps) {
+    constexpr int E = D / 64;
+    const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int heads = n_q + n_k;
+    if (wid >= (long long)M * heads) return;
+    const long long m = wid / heads; const int h = (int)(wid % heads);
+    bf16* gp = dqkv + m * ldd + (long long)h * D;
+    const bf16* xp = pre + m * ldp + (long long)h * D;
+    const bf16* w = (h < n_q) ? qw : kw;
+    const float position = (float)pos[m];
+    float da[E], db[E], xa[E], xb[E], dna[E], dnb[E];
+    float ss = 0.f, dot = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int j = lane * E + e;
+        const float inv_freq = 1.0f / powf(theta, (float)(2 * j) / (float)D);
+        float sn, cs;
+        sincosf(position * inv_freq, &sn, &cs);
+        sn = rbf(sn); cs = rbf(cs);
+        const float glo = __bfloat162float(gp[j]), ghi = __bfloat162float(gp[D / 2 + j]);
+        da[e] = glo * cs + ghi * sn;                     // R(-theta) dy
+        db[e] = -glo * sn + ghi * cs;
+        xa[e] = __bfloat162float(xp[j]); xb[e] = __bfloat162float(xp[D / 2 + j]);
+        ss += xa[e] * xa[e] + xb[e] * xb[e];
+        dna[e] = da[e] * __bfloat162float(w[j]); dnb[e] = db[e] * __bfloat162float(w[D / 2 + j]);
+        dot += dna[e] * xa[e] + dnb[e] * xb[e];
+    }
+    ss = br::warp_sum(ss); dot = br::warp_sum(dot);
+    const float r = rsqrtf(ss / (float)D + eps);
+    const float c = dot * r * r * r / (float)D;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int j = lane * E + e;
+        gp[j] = __float2bfloat16(r * dna[e] - xa[e] * c);
+        gp[D / 2 + j] = __float2bfloat16(r * dnb[e] - xb[e] * c);
+    }
+}
+
+// out[P, Rr] (+)= sum_m big[m, p] * small[m, r]; CTA = 64 p-columns x one chunk of rows; fp32 atomics across chunks.
+// big columns are addressed in 16-byte chunks: chunk c -> element offset (c * chunk_stride + chunk_offset) * 8
+// (chunk_stride 2 selects the gate or the up half of the blocked gate/up layout).
+template <int RR>
+__global__ void __launch_bounds__(128) xty_kernel(const bf16* __restrict__ big, long long ldb, const bf16* __restrict__ small, long long lds,
+                                                  float* __restrict__ out, long long ldo, int M, int P, int rows_per_cta, int chunk_stride,
+                                                  int chunk_offset, int transpose_out) {
+    using namespace attn;
+    constexpr int RCH = RR / 8;
+    __shared__ __align__(128) uint8_t sB[2][64 * 64 * 2];       // [m][p] 64 x 64 bf16
+    __shared__ __align__(128) uint8_t sS[2][64 * RR * 2];       // [m][r]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int p0 = blockIdx.x * 64;
+    const int m_lo = blockIdx.y * rows_per_cta, m_hi = min(M, m_lo + rows_per_cta);
+    float acc[RR / 8][4];
+#pragma unroll
+    for (int i = 0; i < RR / 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    auto issue = [&](int m0, int st) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                         // 64 rows x 8 chunks
+            const int c = tid + i * 128, r = c >> 3, ch = c & 7;
+            const bool ok = (m0 + r) < m_hi;
+            const bf16* src = big + (long long)(ok ? m0 + r : 0) * ldb + ((long long)(p0 / 8 + ch) * chunk_stride + chunk_offset) * 8;
+            cp_async16(sB[st] + ((r * 8 + (ch ^ (r & 7))) << 4), src, ok);
+        }
+        for (int c = tid; c < 64 * RCH; c += 128) {
+            const int r = c / RCH, ch = c % RCH;
+            const bool ok = (m0 + r) < m_hi;
+            const bf16* src = small + (long long)(ok ? m0 + r : 0) * lds + ch * 8;
+            cp_async16(sS[st] + ((r * RCH + (RCH >= 8 ? (ch ^ (r & 7)) : ch)) << 4), src, ok);
+        }
+    };
+    const int n_it = (m_hi - m_lo + 63) / 64;
+    if (n_it > 0) issue(m_lo, 0);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1;
+        if (it + 1 < n_it) issue(m_lo + (it + 1) * 64, st ^ 1);
+        cp_async_commit();
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {                      // 16 rows of m per k-step
+            uint32_t a[4];
+            {   // A[p][m] = big[m][p]: transposed fragments from the [m][p] tile
+                const int r = kk * 16 + (lane & 7) + (lane >> 4) * 8, ch = warp * 2 + ((lane >> 3) & 1);
+                ldsm_x4_t(a, sB[st] + ((r * 8 + (ch ^ (r & 7))) << 4));
+            }
+#pragma unroll
+            for (int np = 0; np < RR / 16; ++np) {
+                uint32_t f[4];
+                const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, ch = np * 2 + (lane >> 4);
+                ldsm_x4_t(f, sS[st] + ((r * RCH + (RCH >= 8 ? (ch ^ (r & 7)) : ch)) << 4));
+                mma16816(acc[2 * np], a, f[0], f[1]);
+                mma16816(acc[2 * np + 1], a, f[2], f[3]);
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+    }
+    const int pa = p0 + warp * 16 + g, pb = pa + 8;
+#pragma unroll
+    for (int nt = 0; nt < RR / 8; ++nt) {
+        const int r = nt * 8 + 2 * t;
+        if (transpose_out) {
+            if (pa < P) { atomicAdd(out + (long long)r * ldo + pa, acc[nt][0]); atomicAdd(out + (long long)(r + 1) * ldo + pa, acc[nt][1]); }
+            if (pb < P) { atomicAdd(out + (long long)r * ldo + pb, acc[nt][2]); atomicAdd(out + (long long)(r + 1) * ldo + pb, acc[nt][3]); }
+        } else {
+            if (pa < P) { atomicAdd(out + (long long)pa * ldo + r, acc[nt][0]); atomicAdd(out + (long long)pa * ldo + r + 1, acc[nt][1]); }
+            if (pb < P) { atomicAdd(out + (long long)pb * ldo + r, acc[nt][2]); atomicAdd(out + (long long)pb * ldo + r + 1, acc[nt][3]); }
+        }
+    }
+}
+
+// out[N, M] = in[M, N]^T (bf16), rows of `out` beyond... (plain tiled transpose; out row stride ldo >= M)
+__global__ void transpose_kernel(const bf16* __restrict__ in, long long ldi, bf16* __restrict__ out, long long ldo, int M, int N) {
+    __shared__ bf16 tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = by + j, c = bx + threadIdx.x;
+        tile[j][threadIdx.x] = (r < M && c < N) ? in[(long long)r * ldi + c] : __float2bfloat16(0.f);
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = bx + j, c = by + threadIdx.x;      // out[r = n][c = m]
+        if (r < N && c < M) out[(long long)r * ldo + c] = tile[threadIdx.x][j];
+    }
+}
+
+// out[n] (+)= sum_m in[m, n]  (fp32 out)
+__global__ void colsum_kernel(const bf16* __restrict__ in, long long ldi, float* __restrict__ out, int M, int N, int rows_per_cta) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int m_lo = blockIdx.y * rows_per_cta, m_hi = min(M, m_lo + rows_per_cta);
+    float s = 0.f;
+    for (int m = m_lo; m < m_hi; ++m) s += __bfloat162float(in[(long long)m * ldi + n]);
+    atomicAdd(out + n, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int br_rmsnorm_bwd(const void* x, int64_t ldx, const void* w, const float* rstd, const void* dy, int64_t lddy, const void* dres, int64_t lddr,
+                   void* dx, int64_t lddx, int M, int d, void* stream) {
+    BR_CHECK_ARG(M > 0 && d % 8 == 0 && d <= 32 * 8 * 16, "rmsnorm_bwd: d=%d must be a multiple of 8, <= 4096", d);
+    const int iters = (d / 8 + 31) / 32;
+    const int wpb = 8;
+    dim3 grid((M + wpb - 1) / wpb);
+    cudaStream_t st = (cudaStream_t)stream;
+#define RB(V) rmsnorm_bwd_kernel<V><<<grid, wpb * 32, 0, st>>>((const bf16*)x, ldx, (const bf16*)w, rstd, (const bf16*)dy, lddy, (const bf16*)dres, lddr, (bf16*)dx, lddx, M, d)
+    if (iters <= 1) RB(1); else if (iters <= 4) RB(4); else if (iters <= 8) RB(8); else RB(16);
+#undef RB
+    BR_CHECK_LAUNCH();
+    return BR_OK;
+}
+
+int br_swiglu_bwd(const void* gu, int64_t ldgu, const void* dact, int64_t ldda, void* dgu, int64_t lddgu, int M, int F, void* stream) {
+    BR_CHECK_ARG(M > 0 && F % 8 == 0, "swiglu_bwd: F %% 8");
+    const long long n = (long long)M * (F / 8);
+    swiglu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)gu, ldgu, (const bf16*)dact, ldda, (bf16*)dgu, lddgu, M, F);
+    BR_CHECK_LAUNCH();
+    return BR_OK;
+}
+
+int br_qk_rope_bwd(void* dqkv, int64_t ldd, const void* qk_pre, int64_t ldp, int M, int n_q_heads, int n_k_heads, int head_dim, const void* q_norm_w,
+                   const void* k_norm_w, const int32_t* positions, float theta, float eps, void* stream) {
+    BR_CHECK_ARG(head_dim == 128 && q_norm_w && k_norm_w, "qk_rope_bwd: Qwen3 layout (head_dim 128, q/k norms) only");
+    const long long warps = (long long)M * (n_q_heads + n_k_heads); const int wpb = 8;
+    qk_rope_bwd_kernel<128><<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        (bf16*)dqkv, ldd, (const bf16*)qk_pre, ldp, M, n_q_heads, n_k_heads, (const bf16*)q_norm_w, (const bf16*)k_norm_w, positions, theta, eps);
+    BR_CHECK_LAUNCH();
+    return BR_OK;
+}
+
+int br_xty_accumulate(const void* big, int64_t ldb, const void* small, int64_t lds, float* out, int64_t ldo, int M, int P, int Rr, int chunk_stride,
+                      int chunk_offset, int transpose_out, void* stream) {
+    BR_CHECK_ARG(M > 0 && P % 64 == 0 && (Rr == 16 || Rr == 32 || Rr == 64), "xty: P %% 64 == 0 and Rr in {16, 32, 64} (P=%d Rr=%d)", P, Rr);
+    BR_CHECK_ARG(ldb % 8 == 0 && lds % 8 == 0, "xty: strides %% 8");
+    int chunks = (4 * br_num_sms() + (P / 64) - 1) / (P / 64);
+    int rows_per_cta = ((M + chunks - 1) / chunks + 63) / 64 * 64;
+    if (rows_per_cta < 256) rows_per_cta = 256;
+    dim3 grid(P / 64, (M + rows_per_cta - 1) / rows_per_cta);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Rr == 16) xty_kernel<16><<<grid, 128, 0, st>>>((const bf16*)big, ldb, (const bf16*)small, lds, out, ldo, M, P, rows_per_cta, chunk_stride, chunk_offset, transpose_out);
+    else if (Rr == 32) xty_kernel<32><<<grid, 128, 0, st>>>((const bf16*)big, ldb, (const bf16*)small, lds, out, ldo, M, P, rows_per_cta, chunk_stride, chunk_offset, transpose_out);
+    else xty_kernel<64><<<grid, 128, 0, st>>>((const bf16*)big, ldb, (const bf16*)small, lds, out, ldo, M, P, rows_per_cta, chunk_stride, chunk_offset, transpose_out);
+    BR_CHECK_LAUNCH();
+    return BR_OK;
+}
+
+int br_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int M, int N, void* stream) {
+    BR_CHECK_ARG(M > 0 && N > 0, "transpose: empty");
+    dim3 grid((N + 31) / 32, (M + 31) / 32), block(32, 8);
+    transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const bf16*)in, ldi, (bf16*)out, ldo, M, N);
+    BR_CHECK_LAUNCH();
+    return BR_OK;
+}
+
+int br_colsum_accumulate(const void* in, int64_t ldi, float* out, int M, int N, void* stream) {
+    BR_CHECK_ARG(M > 0 && N > 0, "colsum: empty");
+    const int rows_per_cta = 512;
+    dim3 grid((N + 255) / 256, (M + rows_per_cta - 1) / rows_per_cta);
+    colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)in, ldi, out, M, N, rows_per_cta);
+    BR_CHECK_LAUNCH();
+    return BR_OK;
+}
+
+}  // extern "C"

@@ -9,7 +9,7 @@
 //     16-byte register chunks feed the mma fragments directly (no shared-memory staging of weights);
 //   * split-K across CTAs with fp32 atomics into a scratch tile + "last CTA does the epilogue and re-zeros" so that
 //     small-N layers (o_proj, down_proj: 160 row tiles) still put >1000 CTAs in flight.
-// Epilogues: bf16 store, +residual, SwiGLU on interleaved (gate, up) rows, fp32 logits.
+// Epilogues: bf16 store, +residual, SwiGLU on (8 gate | 8 up) row blocks, fp32 logits.
 #include "br_common.cuh"
 #include "../../include/bioreason_b200.h"
 
@@ -46,7 +46,7 @@ __device__ __forceinline__ void epilogue(const SkinnyParams& p, const float* til
         for (int idx = threadIdx.x; idx < 8 * NB * 8; idx += blockDim.x) {
             const int r = idx >> 3, j = idx & 7;
             if (r >= R) continue;
-            const float g = rbf(tile[r * 16 + 2 * j]), u = rbf(tile[r * 16 + 2 * j + 1]);
+            const float g = rbf(tile[r * 16 + j]), u = rbf(tile[r * 16 + 8 + j]);   // rows 0-7 gate, 8-15 up
             const float sg = rbf(g / (1.f + __expf(-g)));
             reinterpret_cast<bf16*>(p.out)[(long long)r * p.ldo + (n0 >> 1) + j] = __float2bfloat16(sg * u);
         }

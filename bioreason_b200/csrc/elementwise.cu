@@ -187,15 +187,16 @@ __global__ void scatter_rows_kernel(const bf16* __restrict__ src, long long lds,
     for (int i = lane; i < (d >> 3); i += 32) t[i] = s[i];
 }
 
-// out[m] = src[idx[m]]
+// out[m] = src[idx[m]]  (idx < 0 -> zeros)
 __global__ void gather_rows_kernel(const bf16* __restrict__ src, long long lds, const int* __restrict__ idx, bf16* __restrict__ dst,
                                    long long ldd, int M, int d) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
-    const uint4* s = reinterpret_cast<const uint4*>(src + (long long)idx[row] * lds);
+    const int ix = idx[row];
+    const uint4* s = reinterpret_cast<const uint4*>(src + (long long)(ix < 0 ? 0 : ix) * lds);
     uint4* t = reinterpret_cast<uint4*>(dst + (long long)row * ldd);
-    for (int i = lane; i < (d >> 3); i += 32) t[i] = __ldg(s + i);
+    for (int i = lane; i < (d >> 3); i += 32) t[i] = ix < 0 ? make_uint4(0, 0, 0, 0) : __ldg(s + i);
 }
 
 }  // namespace

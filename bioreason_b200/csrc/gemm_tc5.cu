@@ -29,7 +29,7 @@ struct GemmParams {
     const void* bias; int bias_f32;
     const bf16* residual; long long ldr;
     float alpha;
-    int act;                 // 1: out[j] = silu(acc[2j]) * acc[2j+1]
+    int act;                 // 1: gated SiLU over column blocks of 16 = 8 gate | 8 up -> 8 outputs
     int out_f32;
     const int* row_map;
     bf16* aux; long long ld_aux;   // act==1: raw (pre-activation) accumulator pairs, bf16 [M, N]
@@ -202,8 +202,10 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         float o[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            // HF computes act_fn(gate) in bf16 then multiplies: round the same places
-                            float g = __bfloat162float(__float2bfloat16(v[2 * i])), u = __bfloat162float(__float2bfloat16(v[2 * i + 1]));
+                            // columns come in blocks of 16 = 8 gate | 8 up (packing.py); HF computes act_fn(gate) in bf16
+                            // then multiplies: round at the same places
+                            const int gi = (i >> 3) * 16 + (i & 7);
+                            float g = __bfloat162float(__float2bfloat16(v[gi])), u = __bfloat162float(__float2bfloat16(v[gi + 8]));
                             float sg = __bfloat162float(__float2bfloat16(g / (1.f + __expf(-g))));
                             o[i] = sg * u;
                         }

@@ -22,7 +22,7 @@ import torch.nn as nn
 from .. import engine, ops
 from ..configs import dna_config as _dna_config
 from ..configs import text_config as _text_config
-from ..packing import pack_decoder, pack_encoder
+from ..packing import gu_views, pack_decoder, pack_encoder, refresh_decoder_gu
 
 _TEXT_ALIASES = {"Qwen/Qwen3-4B": "qwen3-4b", "Qwen/Qwen3-1.7B": "qwen3-1.7b"}
 _DNA_ALIASES = {"InstaDeepAI/nucleotide-transformer-v2-500m-multi-species": "nt-v2-500m"}
@@ -81,6 +81,10 @@ class DNALLMModel(nn.Module):
         self._enc = pack_encoder(self.dna_model, device)
         self._proj_w16 = self._proj_b16 = None
         self._lora = None
+        self._proj_ref = None
+        self._rollout_dec = None
+        self._proj_grad_w = torch.zeros_like(self.dna_projection.weight, dtype=torch.float32)
+        self._proj_grad_b = torch.zeros_like(self.dna_projection.bias, dtype=torch.float32)
         self.sync_projection()
 
     # ------------------------------------------------------------------ construction helpers
@@ -139,15 +143,52 @@ class DNALLMModel(nn.Module):
         with torch.no_grad():
             for layer, Lw in zip(self.dna_model.esm.encoder.layer, self._enc.layers):
                 w = layer.intermediate.dense.weight.data
-                g3 = Lw.w_gu.view(F, 2, -1)
-                g3[:, 0, :].copy_(w[:F]); g3[:, 1, :].copy_(w[F:])
-        self._dec.w_T_stale = True
+                gv, uv = gu_views(Lw.w_gu)
+                gv.copy_(w[:F].view(F // 8, 8, -1)); uv.copy_(w[F:].view(F // 8, 8, -1))
+        refresh_decoder_gu(self.text_model, self._dec)
         self.sync_projection()
 
     def sync_projection(self):
         """bf16 compute copy of the (fp32 master) projector; call after every optimizer step."""
         self._proj_w16 = self.dna_projection.weight.detach().to(torch.bfloat16).contiguous()
         self._proj_b16 = self.dna_projection.bias.detach().to(torch.bfloat16).contiguous()
+
+    # ------------------------------------------------------------------ adapters / training state
+    def enable_lora(self, r: int = 32, alpha: float = 64.0, seed: int = 0):
+        """What `get_peft_model(model.text_model, LoraConfig(r=32, lora_alpha=64, target_modules=<all linears>))`
+        does in reason.py:376-388, in kernel layout.  Freezes the base text model and the DNA encoder."""
+        from ..lora import LoraState
+        self._lora = LoraState(self.text_model, self._dec, r, alpha, seed)
+        for p in self.dna_model.parameters():
+            p.requires_grad_(False)                                          # reason.py:371-372
+        self._proj_ref = (self._proj_w16.clone(), self._proj_b16.clone())    # the reference policy's projector (deep copy at init)
+        self._dec.build_transposes()
+        return self._lora
+
+    def trainable_parameters(self):
+        ps = list(self._lora.params) if self._lora is not None else []
+        return ps + [self.dna_projection.weight, self.dna_projection.bias]
+
+    def zero_grad_buffers(self):
+        if self._lora is not None:
+            self._lora.zero_grad()
+        self._proj_grad_w.zero_(); self._proj_grad_b.zero_()
+
+    def attach_grads(self):
+        """Point every trainable parameter's .grad at the buffers the backward kernels accumulated into."""
+        if self._lora is not None:
+            self._lora.attach_grads()
+        self.dna_projection.weight.grad = self._proj_grad_w
+        self.dna_projection.bias.grad = self._proj_grad_b
+
+    def sync_adapters(self, rollout: bool = True):
+        """After an optimizer step: refresh the bf16 kernel-layout copies (LoRA, projector) and the merged rollout weights."""
+        self.sync_projection()
+        if self._lora is not None:
+            self._lora.sync()
+            if rollout:
+                from ..lora import merge_for_rollout
+                self._rollout_dec = merge_for_rollout(self._dec, self._lora, out=self._rollout_dec)
 
     # ------------------------------------------------------------------ hot path
     def merged_embeddings(self, input_ids, dna_tokenized, batch_idx_map, *, return_proj_inputs: bool = False):
@@ -180,7 +221,7 @@ class DNALLMModel(nn.Module):
         emb = self.merged_embeddings(input_ids, dna_tokenized, batch_idx_map)
         ks, ke = engine.mask_window(attention_mask)
         pos = engine.forward_positions(B, L, dev)                           # no position_ids -> arange
-        hidden = engine.decoder_forward(self._dec, emb, B, L, pos, ks, ke, lora=self._lora)
+        hidden = engine.decoder_forward(self._dec, emb, B, L, pos, ks, ke, lora=self._lora.w if self._lora is not None else None)
         loss = None
         if labels is not None:
             loss = self._ce_loss(hidden, labels.to(dev), B, L)

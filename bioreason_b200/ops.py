@@ -289,3 +289,66 @@ def sample_next(logits, *, temperature=1.0, top_k=20, top_p=1.0, do_sample=True,
 
 def decode_advance(step, cur_len):
     check(lib().br_decode_advance(ptr(step, "int32_t*"), ptr(cur_len, "int32_t*"), cur_len.numel(), _stream()), "decode_advance")
+
+
+# ------------------------------------------------------------------ backward
+def attn_bwd(q, k, v, o, dout, lse, dq, dk, dv, B, L, n_q, n_kv, head_dim, *, kv_start=None, kv_end=None, scale=None):
+    if scale is None:
+        scale = head_dim ** -0.5
+    ws = torch.empty(lib().br_attn_bwd_workspace_bytes(B, L, n_q, head_dim), device=q.device, dtype=torch.uint8)
+    check(lib().br_attn_bwd(ptr(q), _row_major_2d(q), ptr(k), _row_major_2d(k), ptr(v), _row_major_2d(v), ptr(o), _row_major_2d(o),
+                            ptr(dout), _row_major_2d(dout), ptr(lse, "float*"), ptr(dq), _row_major_2d(dq), ptr(dk), _row_major_2d(dk),
+                            ptr(dv), _row_major_2d(dv), B, L, n_q, n_kv, head_dim, ptr(kv_start, "int32_t*"), ptr(kv_end, "int32_t*"),
+                            float(scale), ptr(ws), _stream()), "attn_bwd")
+
+
+def rmsnorm_bwd(x, w, rstd, dy, dres=None, out=None):
+    M, d = x.shape
+    if out is None:
+        out = torch.empty(M, d, device=x.device, dtype=torch.bfloat16)
+    check(lib().br_rmsnorm_bwd(ptr(x), _row_major_2d(x), ptr(w), ptr(rstd, "float*"), ptr(dy), _row_major_2d(dy), ptr(dres),
+                               _row_major_2d(dres) if dres is not None else 0, ptr(out), _row_major_2d(out), M, d, _stream()), "rmsnorm_bwd")
+    return out
+
+
+def swiglu_bwd(gu, dact, out=None):
+    M, F2 = gu.shape
+    if out is None:
+        out = torch.empty(M, F2, device=gu.device, dtype=torch.bfloat16)
+    check(lib().br_swiglu_bwd(ptr(gu), _row_major_2d(gu), ptr(dact), _row_major_2d(dact), ptr(out), _row_major_2d(out), M, F2 // 2,
+                              _stream()), "swiglu_bwd")
+    return out
+
+
+def qk_rope_bwd_(dqkv, qk_pre, n_q, n_k, head_dim, q_norm_w, k_norm_w, positions, theta, eps):
+    check(lib().br_qk_rope_bwd(ptr(dqkv), _row_major_2d(dqkv), ptr(qk_pre), _row_major_2d(qk_pre), dqkv.shape[0], n_q, n_k, head_dim,
+                               ptr(q_norm_w), ptr(k_norm_w), ptr(positions, "int32_t*"), float(theta), float(eps), _stream()), "qk_rope_bwd")
+    return dqkv
+
+
+def xty_accumulate_(out, big, small, *, P=None, chunk_stride=1, chunk_offset=0, transpose_out=False):
+    """out (fp32) += big[:, cols]^T @ small; out is [P, Rr] (or [Rr, P] if transpose_out)."""
+    M = big.shape[0]
+    Rr = small.shape[1]
+    if P is None:
+        P = big.shape[1]
+    assert out.dtype == torch.float32 and out.stride(-1) == 1
+    check(lib().br_xty_accumulate(ptr(big), _row_major_2d(big), ptr(small), _row_major_2d(small), ptr(out, "float*"), out.stride(0), M, P, Rr,
+                                  chunk_stride, chunk_offset, 1 if transpose_out else 0, _stream()), "xty_accumulate")
+    return out
+
+
+def transpose(x, out=None, pad_cols_to: int = 8):
+    """bf16 [M, N] -> [N, M'] with M' = M rounded up to `pad_cols_to` (zero padded) so it can feed the TMA GEMM."""
+    M, N = x.shape
+    Mp = (M + pad_cols_to - 1) // pad_cols_to * pad_cols_to
+    if out is None:
+        out = torch.zeros(N, Mp, device=x.device, dtype=torch.bfloat16) if Mp != M else torch.empty(N, Mp, device=x.device, dtype=torch.bfloat16)
+    check(lib().br_transpose_bf16(ptr(x), _row_major_2d(x), ptr(out), _row_major_2d(out), M, N, _stream()), "transpose")
+    return out
+
+
+def colsum_accumulate_(out, x):
+    M, N = x.shape
+    check(lib().br_colsum_accumulate(ptr(x), _row_major_2d(x), ptr(out, "float*"), M, N, _stream()), "colsum")
+    return out

@@ -5,7 +5,8 @@ state_dict keys the reference's callers walk) but their storage 
 buffers laid out for the kernels:
 
   decoder layer : w_qkv [(Hq+2Hkv)*D, d]   rows = q heads | k heads | v heads       (one QKV GEMM)
-                  w_gu  [2F, d]            row 2j = gate_j, row 2j+1 = up_j          (SwiGLU fused in the GEMM epilogue)
+                  w_gu  [2F, d]            blocks of 16 rows = 8 gate rows | 8 up rows (SwiGLU fused in the GEMM epilogue,
+                                           16-byte-aligned gate/up column groups for the backward kernels)
                   w_o   [d, Hq*D], w_down [d, F]
   encoder layer : w_qkv [3*d, d] (+ b_qkv), w_o, w_gu [2F, d] interleaved (x1_j, x2_j), w_down
 Frozen weights additionally get a transposed copy (`*_T`, [in, out]) so that the backward dX GEMMs are also
@@ -17,6 +18,26 @@ from dataclasses import dataclass, field
 from typing import List, Optional
 
 import torch
+
+
+def gu_views(w_gu: torch.Tensor):
+    """(gate, up) views [F/8, 8, ...] of a gate/up-blocked buffer whose leading dim is 2F (blocks of 8 gate | 8 up)."""
+    F2 = w_gu.shape[0]
+    v = w_gu.view(F2 // 16, 2, 8, *w_gu.shape[1:])
+    return v[:, 0], v[:, 1]
+
+
+def _repoint_gu(gate_p, up_p, w_gu):
+    F = gate_p.shape[0]
+    assert F % 8 == 0
+    gv, uv = gu_views(w_gu)
+    with torch.no_grad():
+        gv.copy_(gate_p.data.to(w_gu.dtype).view(F // 8, 8, -1))
+        uv.copy_(up_p.data.to(w_gu.dtype).view(F // 8, 8, -1))
+    # a [F, d] parameter cannot alias the blocked layout as one strided view; the container keeps its own (frozen)
+    # storage and `refresh_gu()` re-derives the kernel copy after a load_state_dict
+    gate_p.data = gate_p.data.to(device=w_gu.device, dtype=w_gu.dtype)
+    up_p.data = up_p.data.to(device=w_gu.device, dtype=w_gu.dtype)
 
 
 def _repoint(param: torch.nn.Parameter, view: torch.Tensor):
@@ -88,9 +109,7 @@ def pack_decoder(model, device="cuda") -> DecoderW:
         w_o = torch.empty(d, Hq * D, device=device, dtype=bf)
         _repoint(at.o_proj.weight, w_o)
         w_gu = torch.empty(2 * F, d, device=device, dtype=bf)
-        gu3 = w_gu.view(F, 2, d)
-        _repoint(mlp.gate_proj.weight, gu3[:, 0, :])
-        _repoint(mlp.up_proj.weight, gu3[:, 1, :])
+        _repoint_gu(mlp.gate_proj.weight, mlp.up_proj.weight, w_gu)
         w_down = torch.empty(d, F, device=device, dtype=bf)
         _repoint(mlp.down_proj.weight, w_down)
         small = {}
@@ -102,6 +121,19 @@ def pack_decoder(model, device="cuda") -> DecoderW:
         W.layers.append(DecoderLayerW(w_qkv=w_qkv, w_o=w_o, w_gu=w_gu, w_down=w_down, **small))
     # buffers (rotary inv_freq) are not used by the kernels; leave them where they are
     return W
+
+
+def refresh_decoder_gu(model, W: DecoderW):
+    """Re-derive the blocked gate/up kernel copies from the container's gate_proj / up_proj (after loading weights)."""
+    with torch.no_grad():
+        for layer, Lw in zip(model.model.layers, W.layers):
+            gv, uv = gu_views(Lw.w_gu)
+            F = layer.mlp.gate_proj.weight.shape[0]
+            gv.copy_(layer.mlp.gate_proj.weight.data.view(F // 8, 8, -1))
+            uv.copy_(layer.mlp.up_proj.weight.data.view(F // 8, 8, -1))
+        for L in W.layers:
+            L.w_qkv_T = L.w_o_T = L.w_gu_T = L.w_down_T = None
+        W.lm_head_T = None
 
 
 @dataclass
@@ -156,18 +188,19 @@ def pack_encoder(model, device="cuda") -> EncoderW:
             _repoint(lin.weight, w_qkv[i * d:(i + 1) * d])
             _repoint(lin.bias, b_qkv[i * d:(i + 1) * d])
         w_gu = torch.empty(2 * F, d, device=device, dtype=bf)
-        gu3 = w_gu.view(F, 2, d)
         inter = layer.intermediate.dense                      # [2F, d]: rows [0,F) = x1 (gate), [F,2F) = x2
+        gv, uv = gu_views(w_gu)
         with torch.no_grad():
-            gu3[:, 0, :].copy_(inter.weight.data[:F].to(bf))
-            gu3[:, 1, :].copy_(inter.weight.data[F:].to(bf))
+            gv.copy_(inter.weight.data[:F].to(bf).view(F // 8, 8, d))
+            uv.copy_(inter.weight.data[F:].to(bf).view(F // 8, 8, d))
         # the container keeps a [2F, d] parameter; give it its own bf16 storage (frozen, forward-only)
         inter.weight.data = inter.weight.data.to(device=device, dtype=bf)
         b_gu = None
         if inter.bias is not None:
             b_gu = torch.empty(2 * F, device=device, dtype=bf)
             with torch.no_grad():
-                b_gu.view(F, 2)[:, 0].copy_(inter.bias.data[:F].to(bf)); b_gu.view(F, 2)[:, 1].copy_(inter.bias.data[F:].to(bf))
+                bg, bu = gu_views(b_gu)
+                bg.copy_(inter.bias.data[:F].to(bf).view(F // 8, 8)); bu.copy_(inter.bias.data[F:].to(bf).view(F // 8, 8))
             inter.bias.data = inter.bias.data.to(device=device, dtype=bf)
         out = layer.output.dense
         W.layers.append(EncoderLayerW(

@@ -54,7 +54,7 @@ typedef struct br_gemm_epilogue {
     const void* residual;    /* bf16 [M, ldr] added after bias (indexed by OUTPUT row) or NULL */
     int64_t ldr;
     float alpha;             /* scales the accumulator first */
-    int32_t act;             /* 0 none; 1: out[:, j] = silu(acc[:, 2j]) * acc[:, 2j+1]  (out width N/2) */
+    int32_t act;             /* 0 none; 1: gated SiLU, columns in blocks of 16 = 8 gate | 8 up: out[:, 8b+i] = silu(acc[:, 16b+i]) * acc[:, 16b+8+i] */
     int32_t out_dtype;       /* BR_BF16 / BR_F32 */
     const int32_t* row_map;  /* optional [M]: output row of input row m (<0: dropped) -- projector scatter */
     void* aux_out;           /* act==1: optional bf16 [M, ld_aux] copy of the pre-activation accumulator */
@@ -99,6 +99,7 @@ int br_qk_rope(void* qkv, int64_t ld, int M, int n_q_heads, int n_k_heads, int h
 int br_embed_gather(const int64_t* ids, const void* table, int64_t ldt, int64_t vocab, void* out, int64_t ldo, int M, int d,
                     const int32_t* keep, void* stream);
 int br_scatter_rows(const void* src, int64_t lds, const int32_t* row_map, void* dst, int64_t ldd, int M, int d, void* stream);
+/* out[m] = src[idx[m]] (idx < 0 -> zero row) */
 int br_gather_rows(const void* src, int64_t lds, const int32_t* idx, void* dst, int64_t ldd, int M, int d, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -118,7 +119,7 @@ int br_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
  * ------------------------------------------------------------------------------------------- */
 int64_t br_skinny_scratch_bytes(int max_N);
 /* out[R, N] = X[R, K] . W[N, K]^T for R <= 32 (HBM-bound weight streaming). mode 0: bf16; 1: bf16(out) + residual;
- * 2: SwiGLU over interleaved (gate, up) rows -> [R, N/2]; 3: fp32.  scratch: zero-initialised once, self-cleaning. */
+ * 2: SwiGLU over (8 gate | 8 up) row blocks -> [R, N/2]; 3: fp32.  scratch: zero-initialised once, self-cleaning. */
 int br_skinny_gemm(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
                    const void* residual, int64_t ldr, void* scratch, void* stream);
 /* per-head q/k RMSNorm + RoPE at position cur_len[r]; K and V of the new token go into the row's page, Q stays in qkv */
@@ -140,6 +141,30 @@ int br_sample_next(const float* logits, int64_t ld, int R, int V, float temperat
                    const float* uniforms, const int32_t* step, int max_steps, int64_t eos_id, int64_t pad_id, int32_t* finished,
                    int64_t* tokens, int64_t* next_ids, void* stream);
 int br_decode_advance(int32_t* step, int32_t* cur_len, int R, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Backward (autograd counterparts; frozen base weights + LoRA adapters, reason.py:362-394)
+ * ------------------------------------------------------------------------------------------- */
+int64_t br_attn_bwd_workspace_bytes(int B, int L, int n_q_heads, int head_dim);
+/* dq/dk/dv (bf16, strided -- typically the three column blocks of one fused dqkv buffer) from dout; causal, head_dim 128 */
+int br_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o, int64_t ldo,
+                const void* dout, int64_t lddo, const float* lse, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv,
+                int64_t lddv, int B, int L, int n_q_heads, int n_kv_heads, int head_dim, const int32_t* kv_start,
+                const int32_t* kv_end, float scale, void* workspace, void* stream);
+/* dx = d(RMSNorm)/dx . dy (+ dres): x, dy, dres, dx bf16 [M, d]; rstd from the forward */
+int br_rmsnorm_bwd(const void* x, int64_t ldx, const void* w, const float* rstd, const void* dy, int64_t lddy, const void* dres,
+                   int64_t lddr, void* dx, int64_t lddx, int M, int d, void* stream);
+/* gu, dgu [M, 2F] in the blocked (8 gate | 8 up) layout; dact [M, F] */
+int br_swiglu_bwd(const void* gu, int64_t ldgu, const void* dact, int64_t ldda, void* dgu, int64_t lddgu, int M, int F, void* stream);
+/* in place on the q and k head columns of dqkv: inverse RoPE then per-head RMSNorm backward (qk_pre = pre-norm q|k) */
+int br_qk_rope_bwd(void* dqkv, int64_t ldd, const void* qk_pre, int64_t ldp, int M, int n_q_heads, int n_k_heads, int head_dim,
+                   const void* q_norm_w, const void* k_norm_w, const int32_t* positions, float theta, float eps, void* stream);
+/* out[P, Rr] += big[M, P]^T . small[M, Rr] (fp32 atomics; LoRA dA / dB).  big columns are taken in 16-byte chunks
+ * (c * chunk_stride + chunk_offset); transpose_out writes out[Rr, P] instead. */
+int br_xty_accumulate(const void* big, int64_t ldb, const void* small, int64_t lds, float* out, int64_t ldo, int M, int P, int Rr,
+                      int chunk_stride, int chunk_offset, int transpose_out, void* stream);
+int br_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int M, int N, void* stream);
+int br_colsum_accumulate(const void* in, int64_t ldi, float* out, int M, int N, void* stream);
 
 #ifdef __cplusplus
 }

@@ -114,7 +114,8 @@ def test_gemm_epilogues(ops):
     # gated SiLU on interleaved (gate, up) column pairs + aux copy of the pre-activation
     aux = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     out = ops.gemm(a.cuda(), b.cuda(), act=1, aux_out=aux).cpu().float()
-    g, u = acc[:, 0::2].bfloat16().float(), acc[:, 1::2].bfloat16().float()
+    a4 = acc.view(M, N // 16, 2, 8)
+    g, u = a4[:, :, 0].reshape(M, N // 2).bfloat16().float(), a4[:, :, 1].reshape(M, N // 2).bfloat16().float()
     ref = torch.nn.functional.silu(g).bfloat16().float() * u
     torch.testing.assert_close(out, ref, rtol=2e-2, atol=2e-2)
     torch.testing.assert_close(aux.cpu().float(), acc, rtol=1e-2, atol=3e-2)
