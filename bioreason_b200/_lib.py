@@ -52,7 +52,12 @@ def last_error() -> str:
     return ffi.string(buf).decode()
 
 
+_KERNELS_PER_CALL = {"lmhead_logprob_fwd": 2, "attn_bwd": 3, "decode_attn": 3}
+COUNTER = [0]
+
+
 def check(rc: int, what: str = ""):
+    COUNTER[0] += _KERNELS_PER_CALL.get(what, 1)
     if rc != 0:
         raise RuntimeError(f"libbioreason_b200 {what} failed ({rc}): {last_error()}")
 

@@ -232,8 +232,11 @@ class RolloutEngine:
             for t, v in zip((tokens, next_ids, finished, step, cur_len), state):
                 t.copy_(v)                                                # the warm-up step is replayed for real below
             graph = torch.cuda.CUDAGraph()
+            n0 = ops.LAUNCHES[0]
             with torch.cuda.graph(graph):
                 decode_step()
+            per_replay = ops.LAUNCHES[0] - n0
+            ops.LAUNCHES[0] = n0
             for t, v in zip((tokens, next_ids, finished, step, cur_len), state):
                 t.copy_(v)
         done_steps = 0
@@ -241,7 +244,11 @@ class RolloutEngine:
         while done_steps < n_steps:
             chunk = min(check_every, n_steps - done_steps) if eos >= 0 else n_steps - done_steps
             for _ in range(chunk):
-                graph.replay() if graph is not None else decode_step()
+                if graph is not None:
+                    graph.replay()
+                    ops.LAUNCHES[0] += per_replay
+                else:
+                    decode_step()
             done_steps += chunk
             if eos >= 0 and done_steps < n_steps and bool(finished.min().item() == 1):
                 break

@@ -9,9 +9,10 @@ from typing import Optional
 
 import torch
 
-from ._lib import check, ffi, lib, ptr
+from ._lib import COUNTER as LAUNCHES_RAW, check, ffi, lib, ptr
 
 BF16, F32 = 0, 1
+LAUNCHES = LAUNCHES_RAW   # kernels launched through the C ABI (bench.py's gpu_launches); graph replays add their captured count
 
 
 def _stream():

@@ -1,0 +1,272 @@
+"""B200-native `DNALLMGRPOTrainer`: the tensor math of bioreason/trainer/grpo_trainer.py on libbioreason_b200.
+
+Kept from the reference: `RepeatRandomSampler` semantics (:72-119), the rollout with the hard-coded sampling config
+(:384-391), EOS-inclusive completion mask (:605-609), ref log-probs with the frozen reference policy, old log-probs only
+when num_iterations > 1 (:617-640), all-gather of rewards then group-normalised advantages with unbiased std and +1e-4
+(:679-699), the clipped-ratio + beta*k3-KL loss with per-row masked mean (:786-812), the metric names (:703-716, :803, :812).
+Re-designed: one fused lm_head+log-softmax+gather kernel instead of [B, L, V] logits; rollout on the paged-KV decode
+engine with the G samples sharing one prefill; hand-written backward; one flat NCCL all-reduce of the LoRA+projector
+gradients.  Not HF-Trainer based (accelerate/trl/peft are not installed in this image).
+"""
+from __future__ import annotations
+
+import time
+from collections import defaultdict
+from typing import Any, Callable, Dict, List, Optional, Sized, Union
+
+import torch
+import torch.distributed as dist
+from torch.utils.data import Sampler
+
+from .. import ops, training
+from .grpo_config import DNALLMGRPOConfig
+
+
+class RepeatRandomSampler(Sampler):
+    """grpo_trainer.py:72-119 -- each index repeated `mini_repeat_count` times, chunks of `batch_size` unique indices,
+    the whole chunk repeated `repeat_count` times; same seed on every rank."""
+
+    def __init__(self, data_source: Sized, mini_repeat_count: int, batch_size: int = 1, repeat_count: int = 1, seed: Optional[int] = None):
+        self.data_source, self.mini_repeat_count, self.batch_size, self.repeat_count = data_source, mini_repeat_count, batch_size, repeat_count
+        self.num_samples = len(data_source)
+        self.seed = seed
+        self.generator = torch.Generator()
+        if seed is not None:
+            self.generator.manual_seed(seed)
+
+    def __iter__(self):
+        indexes = torch.randperm(self.num_samples, generator=self.generator).tolist()
+        indexes = [indexes[i:i + self.batch_size] for i in range(0, len(indexes), self.batch_size)]
+        indexes = [chunk for chunk in indexes if len(chunk) == self.batch_size]
+        for chunk in indexes:
+            for _ in range(self.repeat_count):
+                for index in chunk:
+                    for _ in range(self.mini_repeat_count):
+                        yield index
+
+    def __len__(self) -> int:
+        return self.num_samples * self.mini_repeat_count * self.repeat_count
+
+
+def _world():
+    return (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
+
+
+class DNALLMGRPOTrainer:
+    def __init__(self, model, reward_funcs: Union[Callable, List[Callable]], args: Optional[DNALLMGRPOConfig] = None, dna_module=None,
+                 train_dataset=None, eval_dataset=None, processing_class=None, reward_processing_classes=None, callbacks=None,
+                 optimizers=(None, None), peft_config=None, freeze_dna_modules: bool = False, attn_implementation: str = "flash_attention_2",
+                 torch_dtype: str = "bfloat16", **kwargs):
+        assert not isinstance(model, str), "model must be a DNALLMModel instance"             # grpo_trainer.py:241
+        self.model, self.args = model, args or DNALLMGRPOConfig()
+        a = self.args
+        self.reward_funcs = list(reward_funcs) if isinstance(reward_funcs, (list, tuple)) else [reward_funcs]
+        self.dna_module, self.processing_class = dna_module, processing_class
+        self.train_dataset, self.eval_dataset = train_dataset, eval_dataset
+        self.num_generations, self.max_completion_length = a.num_generations, a.max_completion_length
+        self.beta, self.num_iterations = a.beta, a.num_iterations
+        self.epsilon_low = a.epsilon
+        self.epsilon_high = a.epsilon_high if a.epsilon_high is not None else a.epsilon
+        rank, world = _world()
+        global_bs = a.per_device_train_batch_size * world
+        possible = [n for n in range(2, global_bs + 1) if global_bs % n == 0]
+        if self.num_generations not in possible:                                            # grpo_trainer.py:428-436
+            raise ValueError(f"The global train batch size ({world} x {a.per_device_train_batch_size}) must be evenly divisible by the "
+                             f"number of generations per prompt ({self.num_generations}). Given the current train batch size, the valid "
+                             f"values for the number of generations are: {possible}.")
+        if model._lora is None:
+            model.enable_lora(r=a.lora_r, alpha=a.lora_alpha, seed=a.seed)
+        model.sync_adapters(rollout=True)
+        self.eos_token_id = getattr(processing_class, "eos_token_id", None) if processing_class is not None else None
+        if self.eos_token_id is None:
+            self.eos_token_id = model.text_config.eos_token_id
+        self.pad_token_id = getattr(processing_class, "pad_token_id", None) if processing_class is not None else None
+        if self.pad_token_id is None:
+            self.pad_token_id = model.text_config.pad_token_id
+        # hard-coded exactly like grpo_trainer.py:384-391 (args.temperature/top_p/top_k are NOT consulted there either)
+        self.generation_kwargs = dict(max_new_tokens=self.max_completion_length, do_sample=True, temperature=0.6, top_p=0.95, top_k=20,
+                                      pad_token_id=self.pad_token_id, eos_token_id=None if a.suppress_eos else self.eos_token_id)
+        opt = optimizers[0]
+        if opt is None:
+            opt = torch.optim.AdamW(model.trainable_parameters(), lr=a.learning_rate, betas=(a.adam_beta1, a.adam_beta2), eps=a.adam_epsilon,
+                                    weight_decay=a.weight_decay, fused=True)
+        self.optimizer = opt
+        self._metrics = defaultdict(list)
+        self._buffered_inputs = [None] * a.gradient_accumulation_steps
+        self._step = 0
+        self.global_step = 0
+        # per-rank distinct sampling stream (set_seed(seed, device_specific=True), grpo_trainer.py:451)
+        self._gen = torch.Generator(device="cuda")
+        self._gen.manual_seed(a.seed + rank)
+        self.timings = defaultdict(float)
+
+    # ------------------------------------------------------------------ data
+    def _get_train_sampler(self):                                                          # grpo_trainer.py:883-897
+        _, world = _world()
+        a = self.args
+        eff = a.per_device_train_batch_size * world * a.gradient_accumulation_steps
+        return RepeatRandomSampler(self.train_dataset, self.num_generations, eff // self.num_generations, self.num_iterations, a.seed)
+
+    def _prepare_prompt_inputs(self, inputs) -> Dict[str, Any]:
+        """Pre-tokenised batches pass through; raw examples go through dna_module + processor like :538-567."""
+        if isinstance(inputs, dict) and "input_ids" in inputs:
+            return inputs
+        if self.dna_module is None or self.processing_class is None:
+            raise ValueError("raw examples need dna_module and processing_class (no tokenizer files exist offline); pass a tokenised batch")
+        prompts_text = self.dna_module.prepare_prompt(self.processing_class, inputs)
+        dnas = [x["dna_sequences"] for x in inputs]
+        return self.dna_module.prepare_model_inputs(self.processing_class, self.model, prompts_text, dnas, return_tensors="pt", padding=True,
+                                                    padding_side="left", add_special_tokens=False)
+
+    # ------------------------------------------------------------------ log-probs
+    def _get_per_token_logps(self, model, input_ids, attention_mask, keep_last=None, lora="policy", **mm):
+        """grpo_trainer.py:510-520 (+ the [:, P-1:] slice of :779 when keep_last is given), no-grad version."""
+        n = input_ids.shape[1] - 1 if keep_last is None else keep_last
+        with torch.no_grad():
+            lp, _ = training.policy_forward(model, input_ids, attention_mask, mm.get("dna_tokenized"), mm.get("batch_idx_map"), n,
+                                            save=False, lora=lora)
+        return lp
+
+    # ------------------------------------------------------------------ rollout + scoring
+    @torch.no_grad()
+    def _generate_and_score_completions(self, inputs, model, uniforms=None, rewards_per_func=None) -> Dict[str, Any]:
+        t0 = time.perf_counter()
+        pi = self._prepare_prompt_inputs(inputs)
+        dev = model._dec.embed.device
+        prompt_ids, prompt_mask = pi["input_ids"].to(dev), pi["attention_mask"].to(dev)
+        mm = dict(dna_tokenized=pi.get("dna_tokenized"), batch_idx_map=pi.get("batch_idx_map"))
+        B, P = prompt_ids.shape
+        C = self.max_completion_length
+        if uniforms is None:
+            uniforms = torch.rand(C, B, device=dev, generator=self._gen)
+        completion_ids = model.generate(prompt_ids, prompt_mask, mm["dna_tokenized"], mm["batch_idx_map"], uniforms=uniforms, **self.generation_kwargs)
+        self.timings["rollout"] += time.perf_counter() - t0
+        completion_mask = ops.eos_mask(completion_ids, self.eos_token_id if not self.args.suppress_eos else -1)      # :605-609
+        ids = torch.cat([prompt_ids, completion_ids], dim=1)
+        attention_mask = torch.cat([prompt_mask, completion_mask.to(prompt_mask.dtype)], dim=1)                       # :612
+        Cc = completion_ids.shape[1]
+        old_lp = self._get_per_token_logps(model, ids, attention_mask, keep_last=Cc, **mm) if self.num_iterations > 1 else None
+        ref_lp = self._get_per_token_logps(model, ids, attention_mask, keep_last=Cc, lora=None, **mm) if self.beta != 0.0 else None
+        # rewards: token-level callables f(completion_ids=, prompt_ids=, **batch) -> [B] floats (text rewards need a tokenizer)
+        if rewards_per_func is None:
+            rewards_per_func = torch.zeros(B, len(self.reward_funcs), device=dev)
+            for i, f in enumerate(self.reward_funcs):
+                out = f(completion_ids=completion_ids, prompt_ids=prompt_ids, completion_mask=completion_mask)
+                rewards_per_func[:, i] = torch.as_tensor(out, dtype=torch.float32, device=dev)
+        rank, world = _world()
+        if world > 1:                                                                                                 # C1, :679
+            gathered = [torch.empty_like(rewards_per_func) for _ in range(world)]
+            dist.all_gather(gathered, rewards_per_func.contiguous())
+            rewards_all = torch.cat(gathered, 0)
+        else:
+            rewards_all = rewards_per_func
+        adv_all, gmean, gstd = ops.grpo_advantages(rewards_all, self.num_generations, return_stats=True)               # :682-692
+        advantages = adv_all[rank * B:(rank + 1) * B]                                                                  # :695-699
+        self._metrics["completion_length"].append(completion_mask.sum(1).float().mean())
+        self._metrics["reward"].append(rewards_all.sum(1).mean())
+        self._metrics["reward_std"].append(gstd.mean())
+        for i, f in enumerate(self.reward_funcs):
+            self._metrics[f"rewards/{getattr(f, '__name__', 'reward_' + str(i))}"].append(rewards_all[:, i].mean())
+        self.timings["score"] += time.perf_counter() - t0
+        return dict(prompt_ids=prompt_ids, prompt_mask=prompt_mask, completion_ids=completion_ids, completion_mask=completion_mask,
+                    old_per_token_logps=old_lp, ref_per_token_logps=ref_lp, advantages=advantages, multimodal_inputs=mm)
+
+    # ------------------------------------------------------------------ loss (+ backward through the kernels)
+    def compute_loss(self, model, inputs, return_outputs=False, num_items_in_batch=None, backward: bool = True):
+        if return_outputs:
+            raise ValueError("The GRPOTrainer does not support returning outputs")          # grpo_trainer.py:752-753
+        if self.global_step % self.num_iterations == 0 or self._buffered_inputs[self._step % self.args.gradient_accumulation_steps] is None:
+            if "completion_ids" not in inputs:
+                inputs = self._generate_and_score_completions(inputs, model)
+            self._buffered_inputs[self._step % self.args.gradient_accumulation_steps] = inputs
+        else:
+            inputs = self._buffered_inputs[self._step % self.args.gradient_accumulation_steps]
+        self._step += 1
+        prompt_ids, prompt_mask = inputs["prompt_ids"], inputs["prompt_mask"]
+        completion_ids, completion_mask = inputs["completion_ids"], inputs["completion_mask"]
+        mm = inputs["multimodal_inputs"]
+        ids = torch.cat([prompt_ids, completion_ids], dim=1)
+        mask = torch.cat([prompt_mask, completion_mask.to(prompt_mask.dtype)], dim=1)
+        B, C = completion_ids.shape
+        adv, old, ref = inputs["advantages"], inputs["old_per_token_logps"], inputs["ref_per_token_logps"]
+        mr = self.args.micro_rows or B
+        ga = self.args.gradient_accumulation_steps
+        loss_acc = torch.zeros(3, device=ids.device)
+        for lo in range(0, B, mr):
+            hi = min(B, lo + mr)
+            sl = slice(lo, hi)
+            mm_c = _slice_mm(mm, lo, hi)
+            t0 = time.perf_counter()
+            lp, ctx = training.policy_forward(model, ids[sl], mask[sl], mm_c["dna_tokenized"], mm_c["batch_idx_map"], C, save=backward)
+            out3, dlp = ops.grpo_loss_raw(lp, old[sl] if old is not None else None, ref[sl] if ref is not None else None, adv[sl],
+                                          completion_mask[sl], self.beta, self.epsilon_low, self.epsilon_high, want_grad=backward)
+            w = (hi - lo) / B
+            loss_acc += out3 * w                                            # row-mean of row-means is separable over row chunks
+            self.timings["policy_fwd"] += time.perf_counter() - t0
+            if backward:
+                t0 = time.perf_counter()
+                training.policy_backward(model, ctx, dlp * (w / ga))
+                self.timings["policy_bwd"] += time.perf_counter() - t0
+        # clip_ratio is a ratio of sums; with row chunks it is weighted by rows (exact when chunks have equal mask counts)
+        if self.beta > 0:
+            self._metrics["kl"].append(loss_acc[1])
+        self._metrics["clip_ratio"].append(loss_acc[2])
+        return loss_acc[0]
+
+    # ------------------------------------------------------------------ one optimizer step
+    def training_step(self, inputs) -> torch.Tensor:
+        model = self.model
+        if self._step % self.args.gradient_accumulation_steps == 0:
+            model.zero_grad_buffers()
+        loss = self.compute_loss(model, inputs)
+        if self._step % self.args.gradient_accumulation_steps == 0:
+            self._optimizer_step()
+        return loss
+
+    def _optimizer_step(self):
+        model = self.model
+        t0 = time.perf_counter()
+        rank, world = _world()
+        if world > 1:                                                        # C2: one flat bucket, sum then / world (DDP average)
+            bufs = [model._lora.flat_grad, model._proj_grad_w, model._proj_grad_b]
+            for b in bufs:
+                dist.all_reduce(b)
+                b.div_(world)
+        model.attach_grads()
+        if self.args.max_grad_norm and self.args.max_grad_norm > 0:
+            torch.nn.utils.clip_grad_norm_(model.trainable_parameters(), self.args.max_grad_norm, foreach=True)
+        self.optimizer.step()
+        model.sync_adapters(rollout=True)
+        self.global_step += 1
+        self.timings["optimizer"] += time.perf_counter() - t0
+
+    def train(self, batches=None, max_steps: Optional[int] = None):
+        """Iterate tokenised batches (or the dataset through RepeatRandomSampler) for max_steps optimizer steps."""
+        a = self.args
+        steps = max_steps if max_steps is not None else (a.max_steps if a.max_steps > 0 else None)
+        if batches is None:
+            sampler = list(iter(self._get_train_sampler()))
+            rank, world = _world()
+            per = a.per_device_train_batch_size
+            batches = ([self.train_dataset[i] for i in sampler[s + rank * per: s + (rank + 1) * per]] for s in range(0, len(sampler), per * world))
+        out = []
+        for b in batches:
+            out.append(self.training_step(b))
+            if steps is not None and self.global_step >= steps:
+                break
+        return out
+
+    def log_metrics(self) -> Dict[str, float]:
+        m = {k: float(torch.stack([torch.as_tensor(x, dtype=torch.float32, device="cuda") for x in v]).mean()) for k, v in self._metrics.items()}
+        self._metrics.clear()
+        return m
+
+
+def _slice_mm(mm, lo, hi):
+    """Row-chunk the multimodal inputs (dna rows follow batch_idx_map)."""
+    if mm.get("dna_tokenized") is None or not mm.get("batch_idx_map"):
+        return dict(dna_tokenized=None, batch_idx_map=[])
+    idx = [i for i, b in enumerate(mm["batch_idx_map"]) if lo <= b < hi]
+    it = torch.tensor(idx, device=mm["dna_tokenized"]["input_ids"].device)
+    return dict(dna_tokenized={k: v[it] for k, v in mm["dna_tokenized"].items() if k in ("input_ids", "attention_mask")},
+                batch_idx_map=[mm["batch_idx_map"][i] - lo for i in idx])
