@@ -34,6 +34,9 @@ def exported_symbols() -> list[str]:
     return sorted(set(re.findall(r"\b(br_[a-z0-9_]+)\s*\(", _cdef_text())))
 
 
+ffi.cdef(_cdef_text())       # declarations only; the shared object is opened on first use
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -41,7 +44,6 @@ def lib():
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -m bioreason_b200.build` "
                 "(there is no CPU / PyTorch fallback for the hot path)")
-        ffi.cdef(_cdef_text())
         _lib = ffi.dlopen(LIB_PATH)
     return _lib
 

@@ -18,7 +18,7 @@ import torch
 import torch.distributed as dist
 from torch.utils.data import Sampler
 
-from .. import ops, training
+from .. import dp, ops, training
 from .grpo_config import DNALLMGRPOConfig
 
 
@@ -153,15 +153,9 @@ class DNALLMGRPOTrainer:
             for i, f in enumerate(self.reward_funcs):
                 out = f(completion_ids=completion_ids, prompt_ids=prompt_ids, completion_mask=completion_mask)
                 rewards_per_func[:, i] = torch.as_tensor(out, dtype=torch.float32, device=dev)
-        rank, world = _world()
-        if world > 1:                                                                                                 # C1, :679
-            gathered = [torch.empty_like(rewards_per_func) for _ in range(world)]
-            dist.all_gather(gathered, rewards_per_func.contiguous())
-            rewards_all = torch.cat(gathered, 0)
-        else:
-            rewards_all = rewards_per_func
+        rewards_all = dp.gather_rewards(rewards_per_func)                                                              # C1, :679
         adv_all, gmean, gstd = ops.grpo_advantages(rewards_all, self.num_generations, return_stats=True)               # :682-692
-        advantages = adv_all[rank * B:(rank + 1) * B]                                                                  # :695-699
+        advantages = dp.local_slice(adv_all, B)                                                                        # :695-699
         self._metrics["completion_length"].append(completion_mask.sum(1).float().mean())
         self._metrics["reward"].append(rewards_all.sum(1).mean())
         self._metrics["reward_std"].append(gstd.mean())
@@ -226,12 +220,7 @@ class DNALLMGRPOTrainer:
     def _optimizer_step(self):
         model = self.model
         t0 = time.perf_counter()
-        rank, world = _world()
-        if world > 1:                                                        # C2: one flat bucket, sum then / world (DDP average)
-            bufs = [model._lora.flat_grad, model._proj_grad_w, model._proj_grad_b]
-            for b in bufs:
-                dist.all_reduce(b)
-                b.div_(world)
+        dp.allreduce_mean_([model._lora.flat_grad, model._proj_grad_w, model._proj_grad_b])     # C2: sum then / world (DDP average)
         model.attach_grads()
         if self.args.max_grad_norm and self.args.max_grad_norm > 0:
             torch.nn.utils.clip_grad_norm_(model.trainable_parameters(), self.args.max_grad_norm, foreach=True)
@@ -246,9 +235,7 @@ class DNALLMGRPOTrainer:
         steps = max_steps if max_steps is not None else (a.max_steps if a.max_steps > 0 else None)
         if batches is None:
             sampler = list(iter(self._get_train_sampler()))
-            rank, world = _world()
-            per = a.per_device_train_batch_size
-            batches = ([self.train_dataset[i] for i in sampler[s + rank * per: s + (rank + 1) * per]] for s in range(0, len(sampler), per * world))
+            batches = ([self.train_dataset[i] for i in idx] for idx in dp.rank_batches(sampler, a.per_device_train_batch_size))
         out = []
         for b in batches:
             out.append(self.training_step(b))
