@@ -1,0 +1,311 @@
+// One launch per layer per decode step: q/k RMSNorm + RoPE, KV append, prefix-shared + private paged attention and the
+// split combine (replaces br_decode_rope_append + the two br_decode_attn passes + the combine kernel: 4 launches -> 1;
+// the decode step is launch-latency sensitive -- ~360 small launches per token before fusion).
+//
+// Work items (blockIdx.x): first  n_groups*Hkv*SS  "shared" items  (group, kv head, split over the common prompt pages;
+//                                 G x Hq/Hkv query vectors = the M dimension of the mma tiles),
+//                          then   R*Hkv*SP         "private" items (row, kv head, split over the row's own pages).
+// Every item ropes its own query vectors in shared memory (no roped copy of Q in HBM).  The private item whose page range
+// contains the newest position also norm+ropes the new K, copies the new V and appends both to the row's page before
+// loading it.  Partials (O, LSE) go to a workspace; the last item to arrive for a (row, kv head) pair merges them.
+#include "br_common.cuh"
+#include "../../include/bioreason_b200.h"
+#include "attn_common.cuh"
+using namespace attn;
+
+namespace {
+
+__device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+struct FusedParams {
+    const bf16* qkv; long long ld;        // raw (pre-norm, pre-rope) fused QKV of the new tokens [R, ld]
+    const bf16 *qw, *kw;
+    bf16 *kcache, *vcache;
+    const int* page_table; int max_pages;
+    const int* cur_len;
+    int R, G, Hq, Hkv, GQ;
+    int n_shared_pages, SS, SP, n_slots;
+    float* part_o; float* part_lse; int* counters;      // [R,Hq,n_slots,D], [R,Hq,n_slots], [R*Hkv]
+    bf16* out; long long ldo;
+    float scale_log2, theta, eps;
+};
+
+// norm + rope of one 128-wide head vector held as (lo[2], hi[2]) per lane; returns roped values
+template <int D>
+__device__ __forceinline__ void norm_rope(const bf16* __restrict__ src, const bf16* __restrict__ w, int pos, float theta, float eps, int lane,
+                                          float (&olo)[D / 64], float (&ohi)[D / 64]) {
+    constexpr int E = D / 64;
+    float lo[E], hi[E], ss = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        lo[e] = __bfloat162float(src[lane * E + e]); hi[e] = __bfloat162float(src[D / 2 + lane * E + e]);
+        ss += lo[e] * lo[e] + hi[e] * hi[e];
+    }
+    const float rstd = rsqrtf(br::warp_sum(ss) / (float)D + eps);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int j = lane * E + e;
+        const float a = rbf(__bfloat162float(w[j]) * rbf(lo[e] * rstd));
+        const float b = rbf(__bfloat162float(w[D / 2 + j]) * rbf(hi[e] * rstd));
+        const float inv_freq = 1.0f / powf(theta, (float)(2 * j) / (float)D);
+        float sn, cs;
+        sincosf((float)pos * inv_freq, &sn, &cs);
+        sn = rbf(sn); cs = rbf(cs);
+        olo[e] = rbf(a * cs) + rbf(-b * sn);
+        ohi[e] = rbf(b * cs) + rbf(a * sn);
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
+    constexpr int BN = 64, TILE = 64 * D * 2, NT = 64, QROWS = 32, E = D / 64;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sQ = smem;                          // 32 x D
+    uint8_t* sK = smem + QROWS * D * 2;
+    uint8_t* sV = sK + 2 * TILE;
+    __shared__ int s_last[64];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int n_groups = p.R / p.G;
+    const int n_shared_items = (p.n_shared_pages > 0 && p.SS > 0) ? n_groups * p.Hkv * p.SS : 0;
+    int item = blockIdx.x;
+    const bool shared_pass = item < n_shared_items;
+    int split, kvh, row_base, rows_per_unit, n_splits, slot_base;
+    if (shared_pass) {
+        split = item % p.SS; kvh = (item / p.SS) % p.Hkv; row_base = (item / (p.SS * p.Hkv)) * p.G;
+        rows_per_unit = p.G; n_splits = p.SS; slot_base = 0;
+    } else {
+        item -= n_shared_items;
+        split = item % p.SP; kvh = (item / p.SP) % p.Hkv; row_base = item / (p.SP * p.Hkv);
+        rows_per_unit = 1; n_splits = p.SP; slot_base = n_shared_items ? p.SS : 0;
+    }
+    const int n_sh = n_shared_items ? p.n_shared_pages : 0;
+    const int* table = p.page_table + (long long)row_base * p.max_pages;
+    const long long page_stride = (long long)p.Hkv * 64 * D;
+
+    int kv_len = 0, pg_lo, pg_hi;
+    if (shared_pass) { pg_lo = split; pg_hi = n_sh; }
+    else { kv_len = p.cur_len[row_base] + 1; pg_lo = n_sh + split; pg_hi = (kv_len + 63) >> 6; }
+
+    // ---- queries: norm + rope straight into the swizzled smem tile (slot s -> row s / GQ, head kvh*GQ + s % GQ)
+    for (int s = warp; s < QROWS; s += 2) {
+        const int rr = s / p.GQ, hh = kvh * p.GQ + s % p.GQ;
+        const bool ok = rr < rows_per_unit && (row_base + rr) < p.R;
+        float olo[E], ohi[E];
+        if (ok) {
+            const int row = row_base + rr;
+            norm_rope<D>(p.qkv + (long long)row * p.ld + (long long)hh * D, p.qw, p.cur_len[row], p.theta, p.eps, lane, olo, ohi);
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) olo[e] = ohi[e] = 0.f;
+        }
+        // element j = lane*E + e lives in 16-byte chunk j / 8
+        const int j0 = lane * E;
+        *reinterpret_cast<uint32_t*>(tile_ptr<D>(sQ, s, j0 >> 3) + (j0 & 7) * 2) = br::pack_bf16(olo[0], olo[1]);
+        *reinterpret_cast<uint32_t*>(tile_ptr<D>(sQ, s, (D / 2 + j0) >> 3) + (j0 & 7) * 2) = br::pack_bf16(ohi[0], ohi[1]);
+    }
+    // ---- append the new token's K / V (private item that owns the newest page)
+    if (!shared_pass) {
+        const int pos = kv_len - 1;
+        const int last_pg = pos >> 6;
+        if (last_pg >= pg_lo && (last_pg - pg_lo) % n_splits == 0) {
+            const int page = table[last_pg], slot = pos & 63;
+            if (warp == 0) {
+                float olo[E], ohi[E];
+                norm_rope<D>(p.qkv + (long long)row_base * p.ld + (long long)(p.Hq + kvh) * D, p.kw, pos, p.theta, p.eps, lane, olo, ohi);
+                bf16* dst = p.kcache + ((long long)page * p.Hkv + kvh) * 64 * D + (long long)slot * D;
+                const int j0 = lane * E;
+                *reinterpret_cast<uint32_t*>(dst + j0) = br::pack_bf16(olo[0], olo[1]);
+                *reinterpret_cast<uint32_t*>(dst + D / 2 + j0) = br::pack_bf16(ohi[0], ohi[1]);
+            } else {
+                const bf16* src = p.qkv + (long long)row_base * p.ld + (long long)(p.Hq + p.Hkv + kvh) * D;
+                bf16* dst = p.vcache + ((long long)page * p.Hkv + kvh) * 64 * D + (long long)slot * D;
+                if (lane < D / 8) reinterpret_cast<uint4*>(dst)[lane] = reinterpret_cast<const uint4*>(src)[lane];
+            }
+            __threadfence();
+        }
+    }
+    __syncthreads();
+
+    auto tile_src = [&](const bf16* cache, int pg) { return cache + (long long)table[pg] * page_stride + (long long)kvh * 64 * D; };
+    if (pg_lo < pg_hi) {
+        load_tile<D, NT>(sK, tile_src(p.kcache, pg_lo), D, 0, 64, tid);
+        load_tile<D, NT>(sV, tile_src(p.vcache, pg_lo), D, 0, 64, tid);
+    }
+    cp_async_commit();
+
+    uint32_t qf[D / 16][4];
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk)
+        ldsm_x4(qf[kk], tile_ptr<D>(sQ, warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, kk * 2 + (lane >> 4)));
+    cp_async_wait<0>();
+    __syncthreads();
+
+    float o[D / 8][4];
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    const bool warp_live = shared_pass ? (warp * 16 < rows_per_unit * p.GQ) : (warp == 0);
+
+    int it = 0;
+    for (int pg = pg_lo; pg < pg_hi; pg += n_splits, ++it) {
+        const int st = it & 1;
+        uint8_t* cK = sK + st * TILE;
+        uint8_t* cV = sV + st * TILE;
+        if (pg + n_splits < pg_hi) {
+            load_tile<D, NT>(sK + (st ^ 1) * TILE, tile_src(p.kcache, pg + n_splits), D, 0, 64, tid);
+            load_tile<D, NT>(sV + (st ^ 1) * TILE, tile_src(p.vcache, pg + n_splits), D, 0, 64, tid);
+        }
+        cp_async_commit();
+        if (warp_live) {
+            float s[BN / 8][4];
+#pragma unroll
+            for (int i = 0; i < BN / 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+#pragma unroll
+            for (int kk = 0; kk < D / 16; ++kk) {
+#pragma unroll
+                for (int np = 0; np < BN / 16; ++np) {
+                    uint32_t kf[4];
+                    ldsm_x4(kf, tile_ptr<D>(cK, np * 16 + (lane & 7) + (lane >> 4) * 8, kk * 2 + ((lane >> 3) & 1)));
+                    mma16816(s[2 * np], qf[kk], kf[0], kf[1]);
+                    mma16816(s[2 * np + 1], qf[kk], kf[2], kf[3]);
+                }
+            }
+            const int nbase = pg * BN;
+            const bool need_mask = !shared_pass && (nbase + BN > kv_len);
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < BN / 8; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float v = s[nt][e] * p.scale_log2;
+                    if (need_mask) { const int j = nbase + nt * 8 + 2 * t + (e & 1); v = (j < kv_len) ? v : -INFINITY; }
+                    s[nt][e] = v;
+                }
+                mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+                mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+            }
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+            const float ms0 = (mn0 == -INFINITY) ? 0.f : mn0, ms1 = (mn1 == -INFINITY) ? 0.f : mn1;
+            const float a0 = exp2f(m0 - ms0), a1 = exp2f(m1 - ms1);
+            m0 = mn0; m1 = mn1;
+            float rs0 = 0.f, rs1 = 0.f;
+            uint32_t pf[BN / 16][4];
+#pragma unroll
+            for (int nt = 0; nt < BN / 8; ++nt) {
+                const float p0 = exp2f(s[nt][0] - ms0), p1 = exp2f(s[nt][1] - ms0);
+                const float p2 = exp2f(s[nt][2] - ms1), p3 = exp2f(s[nt][3] - ms1);
+                rs0 += p0 + p1; rs1 += p2 + p3;
+                pf[nt >> 1][(nt & 1) * 2 + 0] = br::pack_bf16(p0, p1);
+                pf[nt >> 1][(nt & 1) * 2 + 1] = br::pack_bf16(p2, p3);
+            }
+            l0 = l0 * a0 + rs0; l1 = l1 * a1 + rs1;
+#pragma unroll
+            for (int i = 0; i < D / 8; ++i) { o[i][0] *= a0; o[i][1] *= a0; o[i][2] *= a1; o[i][3] *= a1; }
+#pragma unroll
+            for (int kk = 0; kk < BN / 16; ++kk) {
+#pragma unroll
+                for (int dp = 0; dp < D / 16; ++dp) {
+                    uint32_t vf[4];
+                    ldsm_x4_t(vf, tile_ptr<D>(cV, kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, dp * 2 + (lane >> 4)));
+                    mma16816(o[2 * dp], pf[kk], vf[0], vf[1]);
+                    mma16816(o[2 * dp + 1], pf[kk], vf[2], vf[3]);
+                }
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+    }
+
+    // ---- partials
+    if (warp_live) {
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float LN2 = 0.6931471805599453f;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int s_idx = warp * 16 + g + half * 8;
+            const int rr = s_idx / p.GQ, hh = kvh * p.GQ + s_idx % p.GQ;
+            if (rr >= rows_per_unit || row_base + rr >= p.R) continue;
+            const float l = half ? l1 : l0, m = half ? m1 : m0;
+            const float inv = l > 0.f ? 1.f / l : 0.f;
+            const long long base = ((long long)(row_base + rr) * p.Hq + hh) * p.n_slots + slot_base + split;
+            float* po = p.part_o + base * D;
+#pragma unroll
+            for (int dt = 0; dt < D / 8; ++dt) {
+                const float x = half ? o[dt][2] : o[dt][0], y = half ? o[dt][3] : o[dt][1];
+                __stcg(reinterpret_cast<float2*>(po + dt * 8 + 2 * t), make_float2(x * inv, y * inv));
+            }
+            if (t == 0) __stcg(p.part_lse + base, l > 0.f ? m * LN2 + logf(l) : -INFINITY);
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    // ---- arrival counters: one per (row, kv head); the last arriver merges the n_slots partials of its GQ heads
+    if (tid < rows_per_unit && row_base + tid < p.R)
+        s_last[tid] = (atomicAdd(p.counters + (row_base + tid) * p.Hkv + kvh, 1) == p.n_slots - 1);
+    __syncthreads();
+    for (int rr = 0; rr < rows_per_unit; ++rr) {
+        if (row_base + rr >= p.R || !s_last[rr]) continue;
+        __threadfence();
+        const int row = row_base + rr;
+        for (int idx = tid; idx < p.GQ * D; idx += NT) {
+            const int hq = kvh * p.GQ + idx / D, dd = idx % D;
+            const float* lse = p.part_lse + ((long long)row * p.Hq + hq) * p.n_slots;
+            float mx = -INFINITY;
+            for (int s = 0; s < p.n_slots; ++s) mx = fmaxf(mx, __ldcg(lse + s));
+            float acc = 0.f, den = 0.f;
+            for (int s = 0; s < p.n_slots; ++s) {
+                const float l = __ldcg(lse + s);
+                if (l == -INFINITY) continue;
+                const float w = __expf(l - mx);
+                den += w;
+                acc += w * __ldcg(p.part_o + (((long long)row * p.Hq + hq) * p.n_slots + s) * D + dd);
+            }
+            p.out[(long long)row * p.ldo + (long long)hq * D + dd] = __float2bfloat16(den > 0.f ? acc / den : 0.f);
+        }
+        if (tid == 0) p.counters[row * p.Hkv + kvh] = 0;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t br_decode_fused_workspace_bytes(int R, int n_q_heads, int n_kv_heads, int head_dim, int n_slots) {
+    return (int64_t)R * n_q_heads * n_slots * (head_dim + 1) * sizeof(float) + (int64_t)R * n_kv_heads * sizeof(int);
+}
+
+int br_decode_attn_fused(const void* qkv_raw, int64_t ld, const void* q_norm_w, const void* k_norm_w, void* kcache, void* vcache,
+                         const int32_t* page_table, int max_pages, const int32_t* cur_len, int R, int G, int n_q_heads, int n_kv_heads,
+                         int head_dim, int n_shared_pages, int splits_shared, int splits_private, float scale, float theta, float eps,
+                         void* workspace, void* out, int64_t ldo, void* stream) {
+    BR_CHECK_ARG(head_dim == 128, "decode_attn_fused: head_dim 128 only");
+    BR_CHECK_ARG(R > 0 && G > 0 && R % G == 0 && G <= 64, "decode_attn_fused: R=%d must be a multiple of G=%d (<= 64)", R, G);
+    const int GQ = n_q_heads / n_kv_heads;
+    BR_CHECK_ARG(GQ <= 16 && 16 % GQ == 0 && G * GQ <= 32, "decode_attn_fused: G * Hq/Hkv = %d query vectors per kv head exceed 32", G * GQ);
+    BR_CHECK_ARG(splits_private >= 1 && splits_shared >= 0 && q_norm_w && k_norm_w, "decode_attn_fused: bad arguments");
+    constexpr int D = 128;
+    FusedParams p;
+    p.qkv = (const bf16*)qkv_raw; p.ld = ld; p.qw = (const bf16*)q_norm_w; p.kw = (const bf16*)k_norm_w;
+    p.kcache = (bf16*)kcache; p.vcache = (bf16*)vcache; p.page_table = page_table; p.max_pages = max_pages; p.cur_len = cur_len;
+    p.R = R; p.G = G; p.Hq = n_q_heads; p.Hkv = n_kv_heads; p.GQ = GQ;
+    const int use_shared = (n_shared_pages > 0 && splits_shared > 0) ? 1 : 0;
+    p.n_shared_pages = use_shared ? n_shared_pages : 0; p.SS = use_shared ? splits_shared : 0; p.SP = splits_private;
+    p.n_slots = p.SS + p.SP;
+    p.part_o = (float*)workspace;
+    p.part_lse = p.part_o + (int64_t)R * n_q_heads * p.n_slots * D;
+    p.counters = (int*)(p.part_lse + (int64_t)R * n_q_heads * p.n_slots);
+    p.out = (bf16*)out; p.ldo = ldo; p.scale_log2 = scale * 1.4426950408889634f; p.theta = theta; p.eps = eps;
+    constexpr int SMEM = 32 * D * 2 + 4 * 64 * D * 2;
+    static bool done = false;
+    if (!done) { BR_CHECK_CUDA(cudaFuncSetAttribute(decode_fused_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); done = true; }
+    const int items = (use_shared ? (R / G) * n_kv_heads * p.SS : 0) + R * n_kv_heads * p.SP;
+    decode_fused_kernel<D><<<items, 64, SMEM, (cudaStream_t)stream>>>(p);
+    BR_CHECK_LAUNCH();
+    return BR_OK;
+}
+
+}  // extern "C"

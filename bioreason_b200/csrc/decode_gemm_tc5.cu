@@ -1,0 +1,286 @@
+// Decode-time weight-streaming GEMM on tcgen05 (swap-AB, stream-K, persistent):  out[R, N] = X[R, K] . W[N, K]^T, R <= 32.
+//
+// Every decode step reads every weight byte once (8 GB / step for Qwen3-4B), so the kernel is HBM-bound and is
+// built around bytes in flight, not FLOPs:
+//   * swap-AB: the weight matrix is the M operand (128 output features per UMMA, M=128), the R live rows of X are the N operand
+//     (N = 16 or 32; TMA zero-fills the rows beyond R), accumulator [128 features x N] fp32 in TMEM;
+//   * one persistent CTA per SM; a TMA producer warp keeps a 10-stage ring of 128x64 weight tiles (16 KB each, 128B-swizzled)
+//     in flight -- ~180 KB of outstanding HBM reads per SM independent of occupancy -- an MMA warp issues tcgen05.mma,
+//     4 epilogue warps drain TMEM;
+//   * stream-K: the (feature tile, k block) units of the whole layer are cut into equal contiguous chunks, one per CTA, so
+//     small-N layers (o_proj / down_proj: 20 feature tiles) still load all 148 SMs evenly.  A tile finished by several CTAs
+//     is reduced with fp32 atomics into a scratch tile; the last arriver applies the epilogue and re-zeros the scratch.
+// Epilogues: bf16 store, +residual, SwiGLU over (8 gate | 8 up) feature blocks, fp32 logits.
+#include "br_common.cuh"
+#include "../../include/bioreason_b200.h"
+
+namespace {
+
+constexpr int BM = 128, BK = 64, NTHREADS = 192;
+
+struct SkParams {
+    int R, N, K;
+    int tiles_n, KB, units, chunk;     // units = tiles_n * KB, chunk = units per CTA
+    int mode;                           // 0 bf16, 1 bf16 + residual, 2 SwiGLU blocks, 3 fp32
+    void* out; long long ldo;
+    const bf16* res; long long ldr;
+    float* scratch;                     // [32, N] fp32 (zero between launches)
+    int* counters;                      // [tiles_n]
+    // folded RMSNorm (decode): out[r, :] *= rsqrt(sumsq_in[r] / K + eps) (the norm weight is pre-multiplied into W's columns);
+    // sumsq_out[r] += sum_f out[r, f]^2 over the bf16-rounded outputs (feeds the NEXT folded norm); zero_buf[0..32) = 0.
+    const float* sumsq_in; float* sumsq_out; float* zero_buf; float eps;
+};
+
+__device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+template <int BNX>
+struct SL {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BNX * BK * 2;
+    static constexpr int STAGE = A_BYTES + B_BYTES;
+    static constexpr int NSTAGE = 10;
+    static constexpr int TILE_BYTES = NSTAGE * STAGE;
+    static constexpr int TOTAL = TILE_BYTES + 256 + 1024;
+};
+
+// per-feature epilogue: v[r] = sum for row r of feature f
+template <int BNX>
+__device__ __forceinline__ void apply_epilogue(const SkParams& p, int f, int lane, const float (&v)[BNX]) {
+    const bool f_ok = f < p.N;
+    float rs[BNX];
+#pragma unroll
+    for (int r = 0; r < BNX; ++r) rs[r] = (p.sumsq_in && r < p.R) ? rsqrtf(__ldg(p.sumsq_in + r) / (float)p.K + p.eps) : 1.f;
+    if (p.mode == 2) {
+        // lanes 0-7 / 16-23 hold gate features, 8-15 / 24-31 the matching up features (blocks of 16 features)
+#pragma unroll
+        for (int r = 0; r < BNX; ++r) {
+            const float other = __shfl_down_sync(0xffffffffu, v[r], 8);
+            if (r < p.R && f_ok && (lane & 8) == 0) {
+                const float g = rbf(v[r] * rs[r]), u = rbf(other * rs[r]);
+                const float sg = rbf(g / (1.f + __expf(-g)));
+                reinterpret_cast<bf16*>(p.out)[(long long)r * p.ldo + (f >> 4) * 8 + (f & 7)] = __float2bfloat16(sg * u);
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int r = 0; r < BNX; ++r) {
+        if (r >= p.R) break;                                   // warp-uniform
+        float x = v[r] * rs[r];
+        float sq = 0.f;
+        if (f_ok) {
+            if (p.mode == 3) reinterpret_cast<float*>(p.out)[(long long)r * p.ldo + f] = x;
+            else {
+                if (p.mode == 1) x = rbf(x) + __bfloat162float(p.res[(long long)r * p.ldr + f]);
+                const bf16 xb = __float2bfloat16(x);
+                reinterpret_cast<bf16*>(p.out)[(long long)r * p.ldo + f] = xb;
+                sq = __bfloat162float(xb) * __bfloat162float(xb);
+            }
+        }
+        if (p.sumsq_out) {
+            sq = br::warp_sum(sq);
+            if (lane == 0) atomicAdd(p.sumsq_out + r, sq);
+        }
+    }
+}
+
+template <int BNX>
+__global__ void __launch_bounds__(NTHREADS, 1)
+skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const SkParams p) {
+    using L = SL<BNX>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::TILE_BYTES);
+    uint64_t* empty_bar = full_bar + L::NSTAGE;
+    uint64_t* tfull_bar = empty_bar + L::NSTAGE;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int u_lo = blockIdx.x * p.chunk;
+    const int u_hi = min(p.units, u_lo + p.chunk);
+
+    if (p.zero_buf && blockIdx.x == 0 && threadIdx.x >= 64 && threadIdx.x < 96) p.zero_buf[threadIdx.x - 64] = 0.f;
+    if (warp == 0 && lane == 0) {
+        br::tma_prefetch_desc(&tmW);
+        br::tma_prefetch_desc(&tmX);
+        for (int s = 0; s < L::NSTAGE; ++s) { br::mbar_init(&full_bar[s], 1); br::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { br::mbar_init(&tfull_bar[s], 1); br::mbar_init(&tempty_bar[s], 4); }
+        br::mbar_fence_init();
+    }
+    if (warp == 1) {
+        br::tmem_alloc(tmem_slot, 2 * BNX < 32 ? 32 : 2 * BNX);
+        br::tmem_relinquish();
+    }
+    br::tc_fence_before();
+    __syncthreads();
+    br::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int u = u_lo; u < u_hi; ++u) {
+                const int tile = u / p.KB, kb = u - tile * p.KB;
+                br::mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* sa = smem + s * L::STAGE;
+                br::mbar_expect_tx(&full_bar[s], L::STAGE);
+                br::tma_load_2d(sa, &tmW, &full_bar[s], kb * BK, tile * BM);
+                br::tma_load_2d(sa + L::A_BYTES, &tmX, &full_bar[s], kb * BK, 0);
+                if (++s == L::NSTAGE) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = br::make_idesc_bf16(BM, BNX);
+            int s = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0;
+            int u = u_lo;
+            while (u < u_hi) {
+                const int tile = u / p.KB;
+                const int seg_end = min(u_hi, (tile + 1) * p.KB);
+                br::mbar_wait(&tempty_bar[as], aph ^ 1);
+                br::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BNX;
+                for (int i = 0; u < seg_end; ++u, ++i) {
+                    br::mbar_wait(&full_bar[s], ph);
+                    br::tc_fence_after();
+                    const uint32_t sa = br::smem_u32(smem + s * L::STAGE);
+                    const uint64_t adesc = br::make_sw128_kmajor_desc(sa);
+                    const uint64_t bdesc = br::make_sw128_kmajor_desc(sa + L::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) br::tc_mma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
+                    br::tc_commit(&empty_bar[s]);
+                    if (++s == L::NSTAGE) { s = 0; ph ^= 1; }
+                }
+                br::tc_commit(&tfull_bar[as]);
+                if (++as == 2) { as = 0; aph ^= 1; }
+            }
+        }
+    } else {
+        const int lane_grp = warp & 3;
+        const int et = threadIdx.x - 64;                      // 0..127 within the epilogue group
+        int as = 0; uint32_t aph = 0;
+        int u = u_lo;
+        while (u < u_hi) {
+            const int tile = u / p.KB;
+            const int seg_end = min(u_hi, (tile + 1) * p.KB);
+            const bool whole = (u == tile * p.KB) && (seg_end == (tile + 1) * p.KB);
+            br::mbar_wait(&tfull_bar[as], aph);
+            br::tc_fence_after();
+            const uint32_t taddr = tmem_base + as * BNX + ((uint32_t)(lane_grp * 32) << 16);
+            float v[BNX];
+#pragma unroll
+            for (int c = 0; c < BNX; c += 16) {
+                uint32_t r[16];
+                __syncwarp();
+                tmem_ld_32x16(taddr + c, r);
+                br::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[c + i] = __uint_as_float(r[i]);
+            }
+            br::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) br::mbar_arrive(&tempty_bar[as]);   // accumulator drained into registers
+            if (++as == 2) { as = 0; aph ^= 1; }
+            const int f = tile * BM + lane_grp * 32 + lane;
+            if (whole) {
+                apply_epilogue<BNX>(p, f, lane, v);
+            } else {
+                if (f < p.N) {
+#pragma unroll
+                    for (int r = 0; r < BNX; ++r)
+                        if (r < p.R) atomicAdd(p.scratch + (long long)r * p.N + f, v[r]);
+                }
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) {
+                    const int first = (tile * p.KB) / p.chunk, last = ((tile + 1) * p.KB - 1) / p.chunk;
+                    *s_flag = (atomicAdd(p.counters + tile, 1) == last - first);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (*s_flag) {
+                    __threadfence();
+                    if (f < p.N) {
+#pragma unroll
+                        for (int r = 0; r < BNX; ++r) {
+                            if (r < p.R) { float* sp = p.scratch + (long long)r * p.N + f; v[r] = __ldcg(sp); __stcg(sp, 0.f); } else v[r] = 0.f;
+                        }
+                    }
+                    if (et == 0) p.counters[tile] = 0;
+                    apply_epilogue<BNX>(p, f, lane, v);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");     // s_flag reusable
+            }
+            u = seg_end;
+        }
+    }
+    br::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        br::tc_fence_after();
+        br::tmem_dealloc(tmem_base, 2 * BNX < 32 ? 32 : 2 * BNX);
+    }
+}
+
+template <int BNX>
+int launch(const CUtensorMap& tw, const CUtensorMap& tx, const SkParams& p, int grid, cudaStream_t st) {
+    using L = SL<BNX>;
+    auto kern = skinny_tc5_kernel<BNX>;
+    static bool done = false;
+    if (!done) { BR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL)); done = true; }
+    kern<<<grid, NTHREADS, L::TOTAL, st>>>(tw, tx, p);
+    BR_CHECK_LAUNCH();
+    return BR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t br_skinny_scratch_bytes(int max_N) { return (int64_t)32 * max_N * sizeof(float) + (int64_t)(max_N / 128 + 2) * sizeof(int); }
+
+int br_skinny_gemm_ex(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
+                      const void* residual, int64_t ldr, void* scratch, const float* sumsq_in, float* sumsq_out, float* zero_buf, float eps,
+                      void* stream);
+
+int br_skinny_gemm(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
+                   const void* residual, int64_t ldr, void* scratch, void* stream) {
+    return br_skinny_gemm_ex(X, ldx, W, ldw, out, ldo, R, N, K, mode, residual, ldr, scratch, nullptr, nullptr, nullptr, 0.f, stream);
+}
+
+int br_skinny_gemm_ex(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
+                      const void* residual, int64_t ldr, void* scratch, const float* sumsq_in, float* sumsq_out, float* zero_buf, float eps,
+                      void* stream) {
+    BR_CHECK_ARG(R >= 1 && R <= 32, "skinny_gemm: R=%d must be in [1, 32]", R);
+    BR_CHECK_ARG(N % 16 == 0 && K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "skinny_gemm: N %% 16, K %% 8, ld %% 8 (N=%d K=%d)", N, K);
+    BR_CHECK_ARG(mode >= 0 && mode <= 3 && !(mode == 1 && !residual), "skinny_gemm: bad mode %d", mode);
+    BR_CHECK_ARG(scratch != nullptr, "skinny_gemm: scratch (br_skinny_scratch_bytes, zero-initialised once) is required");
+    SkParams p;
+    p.R = R; p.N = N; p.K = K; p.mode = mode; p.out = out; p.ldo = ldo; p.res = (const bf16*)residual; p.ldr = ldr;
+    p.scratch = (float*)scratch; p.counters = (int*)((float*)scratch + (int64_t)32 * N);
+    p.sumsq_in = sumsq_in; p.sumsq_out = sumsq_out; p.zero_buf = zero_buf; p.eps = eps;
+    BR_CHECK_ARG(!(sumsq_out && mode >= 2), "skinny_gemm: sumsq_out only with bf16 outputs (mode 0/1)");
+    p.tiles_n = (N + BM - 1) / BM; p.KB = (K + BK - 1) / BK; p.units = p.tiles_n * p.KB;
+    int grid = p.units < br_num_sms() ? p.units : br_num_sms();
+    p.chunk = (p.units + grid - 1) / grid;
+    grid = (p.units + p.chunk - 1) / p.chunk;
+    const int BNX = R <= 16 ? 16 : 32;
+    CUtensorMap tw, tx;
+    int rc;
+    if ((rc = br_make_tmap_2d_bf16(&tw, W, N, K, ldw, BM))) return rc;
+    if ((rc = br_make_tmap_2d_bf16(&tx, X, R, K, ldx, BNX))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    return BNX == 16 ? launch<16>(tw, tx, p, grid, st) : launch<32>(tw, tx, p, grid, st);
+}
+
+}  // extern "C"

@@ -163,7 +163,7 @@ __global__ void qk_rope_kernel(bf16* __restrict__ qkv, long long ld, int M, int 
 
 // ---------------------------------------------------------------- embedding gather: out[m] = table[ids[m]] * (mult ? mult[m] : 1)
 __global__ void embed_gather_kernel(const long long* __restrict__ ids, const bf16* __restrict__ table, long long ldt, bf16* __restrict__ out,
-                                    long long ldo, int M, int d, const int* __restrict__ keep, long long vocab) {
+                                    long long ldo, int M, int d, const int* __restrict__ keep, long long vocab, float* __restrict__ sumsq) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -171,7 +171,31 @@ __global__ void embed_gather_kernel(const long long* __restrict__ ids, const bf1
     const bool zero = (keep && keep[row] == 0) || id < 0 || id >= vocab;
     const uint4* src = reinterpret_cast<const uint4*>(table + (zero ? 0 : id) * ldt);
     uint4* dst = reinterpret_cast<uint4*>(out + (long long)row * ldo);
-    for (int i = lane; i < (d >> 3); i += 32) dst[i] = zero ? make_uint4(0, 0, 0, 0) : __ldg(src + i);
+    float ss = 0.f;
+    for (int i = lane; i < (d >> 3); i += 32) {
+        const uint4 v = zero ? make_uint4(0, 0, 0, 0) : __ldg(src + i);
+        dst[i] = v;
+        if (sumsq) {
+            const float2 a = br::unpack_bf16(v.x), b = br::unpack_bf16(v.y), c = br::unpack_bf16(v.z), e = br::unpack_bf16(v.w);
+            ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + e.x * e.x + e.y * e.y;
+        }
+    }
+    if (sumsq) { ss = br::warp_sum(ss); if (lane == 0) sumsq[row] = ss; }
+}
+
+// W[n, k] *= s[k]   (fold a norm weight into the columns of a frozen / merged rollout weight)
+__global__ void scale_columns_kernel(bf16* __restrict__ W, long long ld, long long N, int K, const bf16* __restrict__ s) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one thread per 8 elements
+    const int per_row = K >> 3;
+    if (i >= N * per_row) return;
+    const long long n = i / per_row; const int c = (int)(i % per_row) * 8;
+    uint4* p = reinterpret_cast<uint4*>(W + n * ld + c);
+    const uint4 v = *p, sv = __ldg(reinterpret_cast<const uint4*>(s + c));
+    const uint32_t vs[4] = {v.x, v.y, v.z, v.w}, ss[4] = {sv.x, sv.y, sv.z, sv.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 a = br::unpack_bf16(vs[j]), b = br::unpack_bf16(ss[j]); o[j] = br::pack_bf16(a.x * b.x, a.y * b.y); }
+    *p = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // rows of src copied to dst[row_map[m]] (row_map < 0 skipped)
@@ -251,7 +275,22 @@ int br_qk_rope(void* qkv, int64_t ld, int M, int n_q_heads, int n_k_heads, int h
 int br_embed_gather(const int64_t* ids, const void* table, int64_t ldt, int64_t vocab, void* out, int64_t ldo, int M, int d, const int32_t* keep,
                     void* stream) {
     BR_CHECK_ARG(M > 0 && d % 8 == 0 && ldt % 8 == 0 && ldo % 8 == 0, "embed_gather: d %% 8");
-    ROW_LAUNCH(embed_gather_kernel, M, (const long long*)ids, (const bf16*)table, ldt, (bf16*)out, ldo, M, d, keep, (long long)vocab);
+    ROW_LAUNCH(embed_gather_kernel, M, (const long long*)ids, (const bf16*)table, ldt, (bf16*)out, ldo, M, d, keep, (long long)vocab, (float*)nullptr);
+    return BR_OK;
+}
+
+int br_embed_gather_sumsq(const int64_t* ids, const void* table, int64_t ldt, int64_t vocab, void* out, int64_t ldo, int M, int d, float* sumsq,
+                          void* stream) {
+    BR_CHECK_ARG(M > 0 && d % 8 == 0 && ldt % 8 == 0 && ldo % 8 == 0, "embed_gather_sumsq: d %% 8");
+    ROW_LAUNCH(embed_gather_kernel, M, (const long long*)ids, (const bf16*)table, ldt, (bf16*)out, ldo, M, d, (const int*)nullptr, (long long)vocab, sumsq);
+    return BR_OK;
+}
+
+int br_scale_columns(void* W, int64_t ld, int64_t N, int K, const void* scale, void* stream) {
+    BR_CHECK_ARG(N > 0 && K % 8 == 0 && ld % 8 == 0, "scale_columns: K %% 8");
+    const long long n = N * (K / 8);
+    scale_columns_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((bf16*)W, ld, N, K, (const bf16*)scale);
+    BR_CHECK_LAUNCH();
     return BR_OK;
 }
 

@@ -87,14 +87,20 @@ class RolloutEngine:
 
     # ------------------------------------------------------------------
     def rollout_weights(self) -> DecoderW:
+        """Merged (base + LoRA) weights with the RMSNorm gains folded in -- decode only; the prefill runs the regular
+        forward (base weights + LoRA second K segment)."""
         m = self.model
-        return m._rollout_dec if getattr(m, "_rollout_dec", None) is not None else m._dec
+        if getattr(m, "_rollout_dec", None) is None:
+            from .lora import build_rollout_weights
+            m._rollout_dec = build_rollout_weights(m._dec, m._lora)
+        return m._rollout_dec
 
     @torch.no_grad()
     def generate(self, input_ids, attention_mask, dna_tokenized=None, batch_idx_map=None, *, params: SamplingParams,
                  uniforms: Optional[torch.Tensor] = None, use_graph: bool = True, return_stats: bool = False):
         m = self.model
-        W = self.rollout_weights()
+        W = m._dec                                                          # prefill weights
+        Wd = self.rollout_weights()                                         # decode weights (merged + folded)
         cfg = W.cfg
         dev = W.embed.device
         Hq, Hkv, D, d = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim, cfg.hidden_size
@@ -155,7 +161,7 @@ class RolloutEngine:
                 first = u * P + (P - plen[u])                             # first real token of the left-padded row
                 ops.kv_write_pages(qkv[first:], plen[u], Hq, Hkv, D, pp_dev[u], kc[li], vc[li])
 
-        hidden = engine.decoder_forward(W, emb, U, P, pos, ks, ke, kv_sink=kv_sink)
+        hidden = engine.decoder_forward(W, emb, U, P, pos, ks, ke, kv_sink=kv_sink, lora=m._lora.w if m._lora is not None else None)
         # replicate each group's partially filled tail page to the other G-1 rows
         if G > 1:
             src, dst = [], []
@@ -184,10 +190,14 @@ class RolloutEngine:
         scratch = ops.skinny_scratch(max(cfg.vocab_size, 2 * cfg.intermediate_size), dev)
         splits_shared = min(8, n_shared) if n_shared > 0 else 0
         splits_private = 2 if n_shared > 0 else 8
+        if G * (Hq // Hkv) > 32:
+            raise NotImplementedError("fused decode attention handles G * Hq/Hkv <= 32 query vectors per kv head")
         n_slots = splits_shared + splits_private
-        ws = ops.decode_attn_workspace(R, Hq, D, n_slots, dev)
+        ws = ops.decode_fused_workspace(R, Hq, Hkv, D, n_slots, dev)
         attn_out = torch.empty(R, Hq * D, device=dev, dtype=torch.bfloat16)
         h = torch.empty(R, d, device=dev, dtype=torch.bfloat16)
+        ssq_a = torch.zeros(32, device=dev, dtype=torch.float32)            # sum x^2 of the residual stream entering attention
+        ssq_b = torch.zeros(32, device=dev, dtype=torch.float32)            # ... entering the MLP (ping-pong, see br_skinny_gemm_ex)
 
         def sample(logits):
             ops.sample_next(logits, temperature=params.temperature, top_k=params.top_k, top_p=params.top_p, do_sample=params.do_sample,
@@ -198,24 +208,23 @@ class RolloutEngine:
         # ---- first token from the prefill's last position (row u replicated G times)
         last_rows = torch.tensor([u * P + P - 1 for u in range(U) for _ in range(G)], device=dev, dtype=torch.int32)
         h_last = ops.gather_rows(hidden, last_rows)
-        logits = ops.skinny_gemm(h_last, W.lm_head, scratch, mode=3)
+        logits = ops.skinny_gemm(h_last, W.lm_head, scratch, mode=3)             # prefill output is already final-normed
         sample(logits)
         step += 1                                                         # cur_len stays: the first generated token sits at index plen
 
         def decode_step():
-            ops.embed_gather(next_ids, W.embed, out=h)
+            # 5 launches per layer: qkv GEMM (folded ln1), fused attention, o_proj (+res, sum x^2), gate/up GEMM (folded ln2,
+            # SwiGLU), down_proj (+res, sum x^2); RMSNorm never launches in the decode loop.
+            ops.embed_gather_sumsq(next_ids, Wd.embed, h, ssq_a)
             x = h
-            for li, Lw in enumerate(W.layers):
-                xn = ops.rmsnorm(x, Lw.ln1, eps)
-                qkv = ops.skinny_gemm(xn, Lw.w_qkv, scratch)
-                ops.decode_rope_append(qkv, Hq, Hkv, D, Lw.q_norm, Lw.k_norm, cur_len, table, kc[li], vc[li], theta, eps)
-                ops.decode_attn(qkv, kc[li], vc[li], table, cur_len, G, Hq, Hkv, D, n_shared, splits_shared, splits_private, ws, attn_out)
-                x2 = ops.skinny_gemm(attn_out, Lw.w_o, scratch, mode=1, residual=x)
-                xn2 = ops.rmsnorm(x2, Lw.ln2, eps)
-                act = ops.skinny_gemm(xn2, Lw.w_gu, scratch, mode=2)
-                x = ops.skinny_gemm(act, Lw.w_down, scratch, mode=1, residual=x2)
-            xf = ops.rmsnorm(x, W.final_norm, eps)
-            lg = ops.skinny_gemm(xf, W.lm_head, scratch, mode=3)
+            for li, Lw in enumerate(Wd.layers):
+                qkv = ops.skinny_gemm(x, Lw.w_qkv, scratch, sumsq_in=ssq_a, eps=eps)
+                ops.decode_attn_fused(qkv, Lw.q_norm, Lw.k_norm, kc[li], vc[li], table, cur_len, G, Hq, Hkv, D, n_shared, splits_shared,
+                                      splits_private, theta, eps, ws, attn_out)
+                x2 = ops.skinny_gemm(attn_out, Lw.w_o, scratch, mode=1, residual=x, sumsq_out=ssq_b, zero_buf=ssq_a)
+                act = ops.skinny_gemm(x2, Lw.w_gu, scratch, mode=2, sumsq_in=ssq_b, eps=eps)
+                x = ops.skinny_gemm(act, Lw.w_down, scratch, mode=1, residual=x2, sumsq_out=ssq_a, zero_buf=ssq_b)
+            lg = ops.skinny_gemm(x, Wd.lm_head, scratch, mode=3, sumsq_in=ssq_a, eps=eps)
             sample(lg)
             ops.decode_advance(step, cur_len)
 

@@ -141,21 +141,31 @@ class LoraState:
 
 
 @torch.no_grad()
-def merge_for_rollout(dec_w, lora: LoraState, out=None):
-    """W_eff = W + scale * B A per fused weight (bf16), for the decode kernels (the policy that rolls out is base + LoRA).
-    Uses the tcgen05 GEMM with the base weight as the epilogue residual."""
+def build_rollout_weights(dec_w, lora: "LoraState | None", out=None):
+    """Decode-time weights: W_eff = W + scale * B A per fused weight (the policy that rolls out is base + LoRA; merged with the
+    tcgen05 GEMM, base weight as the epilogue residual), with the RMSNorm gains folded into the columns of the matrices that
+    consume a normed input (w_qkv <- ln1, w_gu <- ln2, lm_head <- final norm) so the decode step needs no norm launches."""
     from . import ops
     from .packing import DecoderLayerW, DecoderW
     if out is None:
-        out = DecoderW(cfg=dec_w.cfg, embed=dec_w.embed, lm_head=dec_w.lm_head, final_norm=dec_w.final_norm)
+        out = DecoderW(cfg=dec_w.cfg, embed=dec_w.embed, lm_head=torch.empty_like(dec_w.lm_head), final_norm=dec_w.final_norm)
+        out.folded = True
         for Lw in dec_w.layers:
             out.layers.append(DecoderLayerW(ln1=Lw.ln1, ln2=Lw.ln2, q_norm=Lw.q_norm, k_norm=Lw.k_norm, w_qkv=torch.empty_like(Lw.w_qkv),
-                                            w_o=torch.empty_like(Lw.w_o), w_gu=torch.empty_like(Lw.w_gu), w_down=torch.empty_like(Lw.w_down)))
-    s = lora.scale
-    for Lw, Ll, T, Lo in zip(dec_w.layers, lora.w.layers, lora.wT, out.layers):
-        # [N, K] = B[N, r'] @ (A^T)[K, r']^T ; K-major operands: A_op = B (K = r'), B_op = A^T ([K, r'])
-        ops.gemm(Ll.b_qkv, T["a_qkv_T"], alpha=s, residual=Lw.w_qkv, out=Lo.w_qkv)
-        ops.gemm(Ll.b_o, T["a_o_T"], alpha=s, residual=Lw.w_o, out=Lo.w_o)
-        ops.gemm(Ll.b_gu, T["a_gu_T"], alpha=s, residual=Lw.w_gu, out=Lo.w_gu)
-        ops.gemm(Ll.b_down, T["a_down_T"], alpha=s, residual=Lw.w_down, out=Lo.w_down)
+                                            w_o=torch.empty_like(Lw.w_o) if lora is not None else Lw.w_o, w_gu=torch.empty_like(Lw.w_gu),
+                                            w_down=torch.empty_like(Lw.w_down) if lora is not None else Lw.w_down))
+        out.lm_head.copy_(dec_w.lm_head)
+        ops.scale_columns_(out.lm_head, dec_w.final_norm)                  # frozen: folded once
+    for i, (Lw, Lo) in enumerate(zip(dec_w.layers, out.layers)):
+        if lora is not None:
+            s, Ll, T = lora.scale, lora.w.layers[i], lora.wT[i]
+            # [N, K] = B[N, r'] @ (A^T)[K, r']^T ; K-major operands: A_op = B (K = r'), B_op = A^T ([K, r'])
+            ops.gemm(Ll.b_qkv, T["a_qkv_T"], alpha=s, residual=Lw.w_qkv, out=Lo.w_qkv)
+            ops.gemm(Ll.b_o, T["a_o_T"], alpha=s, residual=Lw.w_o, out=Lo.w_o)
+            ops.gemm(Ll.b_gu, T["a_gu_T"], alpha=s, residual=Lw.w_gu, out=Lo.w_gu)
+            ops.gemm(Ll.b_down, T["a_down_T"], alpha=s, residual=Lw.w_down, out=Lo.w_down)
+        else:
+            Lo.w_qkv.copy_(Lw.w_qkv); Lo.w_gu.copy_(Lw.w_gu)
+        ops.scale_columns_(Lo.w_qkv, Lw.ln1)
+        ops.scale_columns_(Lo.w_gu, Lw.ln2)
     return out

@@ -146,6 +146,7 @@ class DNALLMModel(nn.Module):
                 gv, uv = gu_views(Lw.w_gu)
                 gv.copy_(w[:F].view(F // 8, 8, -1)); uv.copy_(w[F:].view(F // 8, 8, -1))
         refresh_decoder_gu(self.text_model, self._dec)
+        self._rollout_dec = None
         self.sync_projection()
 
     def sync_projection(self):
@@ -187,8 +188,8 @@ class DNALLMModel(nn.Module):
         if self._lora is not None:
             self._lora.sync()
             if rollout:
-                from ..lora import merge_for_rollout
-                self._rollout_dec = merge_for_rollout(self._dec, self._lora, out=self._rollout_dec)
+                from ..lora import build_rollout_weights
+                self._rollout_dec = build_rollout_weights(self._dec, self._lora, out=self._rollout_dec)
 
     # ------------------------------------------------------------------ hot path
     def merged_embeddings(self, input_ids, dna_tokenized, batch_idx_map, *, return_proj_inputs: bool = False):

@@ -236,8 +236,8 @@ def skinny_scratch(max_n: int, device) -> torch.Tensor:
     return torch.zeros(lib().br_skinny_scratch_bytes(max_n), device=device, dtype=torch.uint8)
 
 
-def skinny_gemm(x, w, scratch, *, mode=0, residual=None, out=None):
-    """out[R, N] = x[R, K] @ w[N, K].T for R <= 32 decode rows."""
+def skinny_gemm(x, w, scratch, *, mode=0, residual=None, out=None, sumsq_in=None, sumsq_out=None, zero_buf=None, eps=0.0):
+    """out[R, N] = x[R, K] @ w[N, K].T for R <= 32 decode rows (optionally with the folded-RMSNorm statistics)."""
     _need_cuda(x, w)
     R, K = x.shape
     N = w.shape[0]
@@ -246,10 +246,24 @@ def skinny_gemm(x, w, scratch, *, mode=0, residual=None, out=None):
             out = torch.empty(R, N, device=x.device, dtype=torch.float32)
         else:
             out = torch.empty(R, N // 2 if mode == 2 else N, device=x.device, dtype=torch.bfloat16)
-    check(lib().br_skinny_gemm(ptr(x), _row_major_2d(x), ptr(w), _row_major_2d(w), ptr(out), _row_major_2d(out), R, N, K, mode,
-                               ptr(residual), _row_major_2d(residual) if residual is not None else 0, ptr(scratch), _stream()),
+    check(lib().br_skinny_gemm_ex(ptr(x), _row_major_2d(x), ptr(w), _row_major_2d(w), ptr(out), _row_major_2d(out), R, N, K, mode,
+                                  ptr(residual), _row_major_2d(residual) if residual is not None else 0, ptr(scratch),
+                                  ptr(sumsq_in, "float*"), ptr(sumsq_out, "float*"), ptr(zero_buf, "float*"), float(eps), _stream()),
           "skinny_gemm")
     return out
+
+
+def embed_gather_sumsq(ids, table, out, sumsq):
+    ids = ids.reshape(-1)
+    assert ids.dtype == torch.int64
+    check(lib().br_embed_gather_sumsq(ptr(ids, "int64_t*"), ptr(table), _row_major_2d(table), table.shape[0], ptr(out), _row_major_2d(out),
+                                      ids.numel(), table.shape[1], ptr(sumsq, "float*"), _stream()), "embed_gather_sumsq")
+    return out
+
+
+def scale_columns_(w, scale):
+    check(lib().br_scale_columns(ptr(w), _row_major_2d(w), w.shape[0], w.shape[1], ptr(scale), _stream()), "scale_columns")
+    return w
 
 
 def decode_rope_append(qkv, n_q, n_kv, head_dim, q_norm_w, k_norm_w, cur_len, page_table, kcache, vcache, theta, eps):
@@ -275,6 +289,22 @@ def decode_attn(qkv, kcache, vcache, page_table, cur_len, G, n_q, n_kv, head_dim
     check(lib().br_decode_attn(ptr(qkv), _row_major_2d(qkv), ptr(kcache), ptr(vcache), ptr(page_table, "int32_t*"), page_table.shape[1],
                                ptr(cur_len, "int32_t*"), R, G, n_q, n_kv, head_dim, n_shared_pages, splits_shared, splits_private,
                                float(scale), ptr(workspace), ptr(out), _row_major_2d(out), _stream()), "decode_attn")
+    return out
+
+
+def decode_fused_workspace(R, n_q, n_kv, head_dim, n_slots, device):
+    return torch.zeros(lib().br_decode_fused_workspace_bytes(R, n_q, n_kv, head_dim, n_slots), device=device, dtype=torch.uint8)
+
+
+def decode_attn_fused(qkv_raw, q_norm_w, k_norm_w, kcache, vcache, page_table, cur_len, G, n_q, n_kv, head_dim, n_shared_pages,
+                      splits_shared, splits_private, theta, eps, workspace, out, scale=None):
+    R = qkv_raw.shape[0]
+    if scale is None:
+        scale = head_dim ** -0.5
+    check(lib().br_decode_attn_fused(ptr(qkv_raw), _row_major_2d(qkv_raw), ptr(q_norm_w), ptr(k_norm_w), ptr(kcache), ptr(vcache),
+                                     ptr(page_table, "int32_t*"), page_table.shape[1], ptr(cur_len, "int32_t*"), R, G, n_q, n_kv,
+                                     head_dim, n_shared_pages, splits_shared, splits_private, float(scale), float(theta), float(eps),
+                                     ptr(workspace), ptr(out), _row_major_2d(out), _stream()), "decode_attn_fused")
     return out
 
 

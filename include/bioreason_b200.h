@@ -122,6 +122,16 @@ int64_t br_skinny_scratch_bytes(int max_N);
  * 2: SwiGLU over (8 gate | 8 up) row blocks -> [R, N/2]; 3: fp32.  scratch: zero-initialised once, self-cleaning. */
 int br_skinny_gemm(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
                    const void* residual, int64_t ldr, void* scratch, void* stream);
+/* Same with a folded RMSNorm for the decode step (norm weight pre-multiplied into W's columns by br_scale_columns):
+ * sumsq_in [R]: out rows are scaled by rsqrt(sumsq_in[r]/K + eps); sumsq_out [R] += sum_f out[r,f]^2 (bf16-rounded, modes 0/1);
+ * zero_buf [32] is cleared (ping-pong statistic buffers).  Any of the three may be NULL. */
+int br_skinny_gemm_ex(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
+                      const void* residual, int64_t ldr, void* scratch, const float* sumsq_in, float* sumsq_out, float* zero_buf,
+                      float eps, void* stream);
+int br_embed_gather_sumsq(const int64_t* ids, const void* table, int64_t ldt, int64_t vocab, void* out, int64_t ldo, int M, int d,
+                          float* sumsq, void* stream);
+/* W[n, k] *= scale[k] in place (bf16) */
+int br_scale_columns(void* W, int64_t ld, int64_t N, int K, const void* scale, void* stream);
 /* per-head q/k RMSNorm + RoPE at position cur_len[r]; K and V of the new token go into the row's page, Q stays in qkv */
 int br_decode_rope_append(void* qkv, int64_t ld, int R, int n_q_heads, int n_kv_heads, int head_dim, const void* q_norm_w,
                           const void* k_norm_w, const int32_t* cur_len, const int32_t* page_table, int max_pages,
@@ -141,6 +151,15 @@ int br_sample_next(const float* logits, int64_t ld, int R, int V, float temperat
                    const float* uniforms, const int32_t* step, int max_steps, int64_t eos_id, int64_t pad_id, int32_t* finished,
                    int64_t* tokens, int64_t* next_ids, void* stream);
 int br_decode_advance(int32_t* step, int32_t* cur_len, int R, void* stream);
+
+/* Fused decode attention (one launch per layer per step): per-head q/k RMSNorm + RoPE at cur_len[r], K/V append to the
+ * row's page, prefix-shared + private paged attention, split merge.  qkv_raw is the un-normalised fused projection of
+ * the new tokens.  workspace: br_decode_fused_workspace_bytes, zero-initialised once (arrival counters are self-resetting). */
+int64_t br_decode_fused_workspace_bytes(int R, int n_q_heads, int n_kv_heads, int head_dim, int n_slots);
+int br_decode_attn_fused(const void* qkv_raw, int64_t ld, const void* q_norm_w, const void* k_norm_w, void* kcache, void* vcache,
+                         const int32_t* page_table, int max_pages, const int32_t* cur_len, int R, int G, int n_q_heads,
+                         int n_kv_heads, int head_dim, int n_shared_pages, int splits_shared, int splits_private, float scale,
+                         float theta, float eps, void* workspace, void* out, int64_t ldo, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Backward (autograd counterparts; frozen base weights + LoRA adapters, reason.py:362-394)

@@ -81,6 +81,7 @@ def test_decode_attention_paged_prefix_shared(ops, U, G, Hq, Hkv, plen, gen):
     qn = (1 + 0.1 * torch.randn(D)).bfloat16().cuda(); kn = (1 + 0.1 * torch.randn(D)).bfloat16().cuda()
     cur = torch.full((R,), T, dtype=torch.int32).cuda()
     # reference for the append: the prefill-path rope kernel at position T
+    raw_qkv = qkv.clone()
     ref_qkv = qkv.clone()
     ops.qk_rope_(ref_qkv, Hq, Hkv, D, cur, 1e6, q_norm_w=qn, k_norm_w=kn, eps=1e-6)
     ops.decode_rope_append(qkv, Hq, Hkv, D, qn, kn, cur, table, kc, vc, 1e6, 1e-6)
@@ -97,6 +98,18 @@ def test_decode_attention_paged_prefix_shared(ops, U, G, Hq, Hkv, plen, gen):
     ops.decode_attn(qkv, kc, vc, table, cur, G, Hq, Hkv, D, n_shared, ss, sp, ws, out)
     ref = _dense_ref(qkv[:, :Hq * D], kd.cuda(), vd.cuda(), cur + 1, Hq, Hkv, D)
     torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
+    # the fused single-launch kernel (rope + append + both passes + merge) on the RAW projection must agree
+    if G * (Hq // Hkv) <= 32:
+        kc2, vc2 = kc.clone(), vc.clone()
+        for r in range(R):                                                 # wipe the appended token: the fused kernel re-appends it
+            pg = table[r, T // PAGE].item()
+            kc2[pg, :, T % PAGE] = 0; vc2[pg, :, T % PAGE] = 0
+        wsf = ops.decode_fused_workspace(R, Hq, Hkv, D, ss + sp, "cuda")
+        out2 = torch.empty_like(out)
+        for _ in range(2):                                                 # twice: arrival counters must self-reset
+            ops.decode_attn_fused(raw_qkv, qn, kn, kc2, vc2, table, cur, G, Hq, Hkv, D, n_shared, ss, sp, 1e6, 1e-6, wsf, out2)
+            torch.testing.assert_close(out2.float(), ref, rtol=2e-2, atol=2e-2)
+        assert torch.equal(kc2, kc) and torch.equal(vc2, vc)
 
 
 def _sampler_ref(logits, T, k, p, u):
