@@ -148,6 +148,13 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---------------- programmatic dependent launch (PDL) ----------------
+// launch_dependents: lets the NEXT kernel in the stream start its prologue (barrier init, TMEM alloc, weight prefetch)
+// while this one is still running; grid_dep_wait: blocks until the PREVIOUS kernel has completed and flushed memory.
+// Everything that reads or writes data shared with earlier kernels must come after grid_dep_wait().
+__device__ __forceinline__ void launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------- misc ----------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -169,6 +176,20 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t v) {
 }
 
 }  // namespace br
+#endif
+
+#ifdef __CUDACC__
+// Launch with the programmatic-stream-serialization attribute (the kernel must call br::grid_dep_wait()).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t br_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 #endif
 
 // Host: 2-D bf16 row-major tensor map, box = {64 cols (128 B, SWIZZLE_128B), box_rows}

@@ -66,6 +66,8 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
     __shared__ int s_last[64];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    br::launch_dependents();
+    br::grid_dep_wait();
     const int n_groups = p.R / p.G;
     const int n_shared_items = (p.n_shared_pages > 0 && p.SS > 0) ? n_groups * p.Hkv * p.SS : 0;
     int item = blockIdx.x;
@@ -247,24 +249,38 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
     if (tid < rows_per_unit && row_base + tid < p.R)
         s_last[tid] = (atomicAdd(p.counters + (row_base + tid) * p.Hkv + kvh, 1) == p.n_slots - 1);
     __syncthreads();
+    // merge: weights w[h][s] = exp(lse - max) / sum are computed once into shared memory; every thread then issues its
+    // n_slots partial loads back to back (independent, 16-byte) instead of a dependent chain of L2 round trips
+    float* s_w = reinterpret_cast<float*>(smem);                      // [GQ][n_slots] (tile smem is free now)
     for (int rr = 0; rr < rows_per_unit; ++rr) {
-        if (row_base + rr >= p.R || !s_last[rr]) continue;
+        if (row_base + rr >= p.R || !s_last[rr]) continue;            // block-uniform
         __threadfence();
         const int row = row_base + rr;
-        for (int idx = tid; idx < p.GQ * D; idx += NT) {
-            const int hq = kvh * p.GQ + idx / D, dd = idx % D;
-            const float* lse = p.part_lse + ((long long)row * p.Hq + hq) * p.n_slots;
+        __syncthreads();
+        if (tid < p.GQ) {
+            const float* lse = p.part_lse + ((long long)row * p.Hq + kvh * p.GQ + tid) * p.n_slots;
+            float l[32];
             float mx = -INFINITY;
-            for (int s = 0; s < p.n_slots; ++s) mx = fmaxf(mx, __ldcg(lse + s));
-            float acc = 0.f, den = 0.f;
+            for (int s = 0; s < p.n_slots; ++s) { l[s] = __ldcg(lse + s); mx = fmaxf(mx, l[s]); }
+            float den = 0.f;
+            for (int s = 0; s < p.n_slots; ++s) { l[s] = (l[s] == -INFINITY) ? 0.f : __expf(l[s] - mx); den += l[s]; }
+            const float inv = den > 0.f ? 1.f / den : 0.f;
+            for (int s = 0; s < p.n_slots; ++s) s_w[tid * p.n_slots + s] = l[s] * inv;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < p.GQ * (D / 4); idx += NT) {
+            const int hl = idx / (D / 4), d4 = (idx % (D / 4)) * 4;
+            const int hq = kvh * p.GQ + hl;
+            const float* po = p.part_o + ((long long)row * p.Hq + hq) * p.n_slots * D + d4;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
             for (int s = 0; s < p.n_slots; ++s) {
-                const float l = __ldcg(lse + s);
-                if (l == -INFINITY) continue;
-                const float w = __expf(l - mx);
-                den += w;
-                acc += w * __ldcg(p.part_o + (((long long)row * p.Hq + hq) * p.n_slots + s) * D + dd);
+                const float w = s_w[hl * p.n_slots + s];
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(po + (long long)s * D));
+                acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
             }
-            p.out[(long long)row * p.ldo + (long long)hq * D + dd] = __float2bfloat16(den > 0.f ? acc / den : 0.f);
+            *reinterpret_cast<uint2*>(p.out + (long long)row * p.ldo + (long long)hq * D + d4) =
+                make_uint2(br::pack_bf16(acc.x, acc.y), br::pack_bf16(acc.z, acc.w));
         }
         if (tid == 0) p.counters[row * p.Hkv + kvh] = 0;
     }
@@ -286,7 +302,7 @@ int br_decode_attn_fused(const void* qkv_raw, int64_t ld, const void* q_norm_w, 
     BR_CHECK_ARG(R > 0 && G > 0 && R % G == 0 && G <= 64, "decode_attn_fused: R=%d must be a multiple of G=%d (<= 64)", R, G);
     const int GQ = n_q_heads / n_kv_heads;
     BR_CHECK_ARG(GQ <= 16 && 16 % GQ == 0 && G * GQ <= 32, "decode_attn_fused: G * Hq/Hkv = %d query vectors per kv head exceed 32", G * GQ);
-    BR_CHECK_ARG(splits_private >= 1 && splits_shared >= 0 && q_norm_w && k_norm_w, "decode_attn_fused: bad arguments");
+    BR_CHECK_ARG(splits_private >= 1 && splits_shared >= 0 && splits_private + splits_shared <= 32 && q_norm_w && k_norm_w, "decode_attn_fused: bad arguments (<= 32 splits)");
     constexpr int D = 128;
     FusedParams p;
     p.qkv = (const bf16*)qkv_raw; p.ld = ld; p.qw = (const bf16*)q_norm_w; p.kw = (const bf16*)k_norm_w;
@@ -303,8 +319,7 @@ int br_decode_attn_fused(const void* qkv_raw, int64_t ld, const void* q_norm_w, 
     static bool done = false;
     if (!done) { BR_CHECK_CUDA(cudaFuncSetAttribute(decode_fused_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); done = true; }
     const int items = (use_shared ? (R / G) * n_kv_heads * p.SS : 0) + R * n_kv_heads * p.SP;
-    decode_fused_kernel<D><<<items, 64, SMEM, (cudaStream_t)stream>>>(p);
-    BR_CHECK_LAUNCH();
+    BR_CHECK_CUDA(br_launch_pdl(decode_fused_kernel<D>, dim3(items), dim3(64), (size_t)SMEM, (cudaStream_t)stream, p));
     return BR_OK;
 }
 

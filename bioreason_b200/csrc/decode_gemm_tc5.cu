@@ -47,7 +47,7 @@ struct SL {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BNX * BK * 2;
     static constexpr int STAGE = A_BYTES + B_BYTES;
-    static constexpr int NSTAGE = 10;
+    static constexpr int NSTAGE = 6;        // 108 KB: two CTAs (this kernel + its PDL successor) fit one SM
     static constexpr int TILE_BYTES = NSTAGE * STAGE;
     static constexpr int TOTAL = TILE_BYTES + 256 + 1024;
 };
@@ -110,7 +110,7 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const int u_lo = blockIdx.x * p.chunk;
     const int u_hi = min(p.units, u_lo + p.chunk);
 
-    if (p.zero_buf && blockIdx.x == 0 && threadIdx.x >= 64 && threadIdx.x < 96) p.zero_buf[threadIdx.x - 64] = 0.f;
+    br::launch_dependents();
     if (warp == 0 && lane == 0) {
         br::tma_prefetch_desc(&tmW);
         br::tma_prefetch_desc(&tmX);
@@ -129,8 +129,21 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 
     if (warp == 0) {
         if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            for (int u = u_lo; u < u_hi; ++u) {
+            // The weights are constant during the rollout: fill the whole ring with weight tiles BEFORE waiting for the
+            // previous kernel (PDL), so the HBM stream of this layer overlaps the tail of the previous kernel.
+            const int n_pre = min(L::NSTAGE, u_hi - u_lo);
+            for (int i = 0; i < n_pre; ++i) {
+                const int u = u_lo + i, tile = u / p.KB, kb = u - tile * p.KB;
+                br::mbar_expect_tx(&full_bar[i], L::STAGE);
+                br::tma_load_2d(smem + i * L::STAGE, &tmW, &full_bar[i], kb * BK, tile * BM);
+            }
+            br::grid_dep_wait();
+            for (int i = 0; i < n_pre; ++i) {
+                const int u = u_lo + i, tile = u / p.KB, kb = u - tile * p.KB;
+                br::tma_load_2d(smem + i * L::STAGE + L::A_BYTES, &tmX, &full_bar[i], kb * BK, 0);
+            }
+            int s = n_pre % L::NSTAGE; uint32_t ph = (n_pre == L::NSTAGE) ? 1u : 0u;
+            for (int u = u_lo + n_pre; u < u_hi; ++u) {
                 const int tile = u / p.KB, kb = u - tile * p.KB;
                 br::mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* sa = smem + s * L::STAGE;
@@ -169,6 +182,8 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     } else {
         const int lane_grp = warp & 3;
         const int et = threadIdx.x - 64;                      // 0..127 within the epilogue group
+        br::grid_dep_wait();                                  // everything below touches data shared with earlier kernels
+        if (p.zero_buf && blockIdx.x == 0 && et < 32) p.zero_buf[et] = 0.f;
         int as = 0; uint32_t aph = 0;
         int u = u_lo;
         while (u < u_hi) {
@@ -238,8 +253,7 @@ int launch(const CUtensorMap& tw, const CUtensorMap& tx, const SkParams& p, int 
     auto kern = skinny_tc5_kernel<BNX>;
     static bool done = false;
     if (!done) { BR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL)); done = true; }
-    kern<<<grid, NTHREADS, L::TOTAL, st>>>(tw, tx, p);
-    BR_CHECK_LAUNCH();
+    BR_CHECK_CUDA(br_launch_pdl(kern, dim3(grid), dim3(NTHREADS), (size_t)L::TOTAL, st, tw, tx, p));
     return BR_OK;
 }
 

@@ -166,6 +166,8 @@ __global__ void embed_gather_kernel(const long long* __restrict__ ids, const bf1
                                     long long ldo, int M, int d, const int* __restrict__ keep, long long vocab, float* __restrict__ sumsq) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    br::launch_dependents();
+    br::grid_dep_wait();
     if (row >= M) return;
     long long id = ids[row];
     const bool zero = (keep && keep[row] == 0) || id < 0 || id >= vocab;
@@ -282,7 +284,8 @@ int br_embed_gather(const int64_t* ids, const void* table, int64_t ldt, int64_t 
 int br_embed_gather_sumsq(const int64_t* ids, const void* table, int64_t ldt, int64_t vocab, void* out, int64_t ldo, int M, int d, float* sumsq,
                           void* stream) {
     BR_CHECK_ARG(M > 0 && d % 8 == 0 && ldt % 8 == 0 && ldo % 8 == 0, "embed_gather_sumsq: d %% 8");
-    ROW_LAUNCH(embed_gather_kernel, M, (const long long*)ids, (const bf16*)table, ldt, (bf16*)out, ldo, M, d, (const int*)nullptr, (long long)vocab, sumsq);
+    BR_CHECK_CUDA(br_launch_pdl(embed_gather_kernel, dim3((M + 7) / 8), dim3(256), 0, (cudaStream_t)stream, (const long long*)ids, (const bf16*)table,
+                                (long long)ldt, (bf16*)out, (long long)ldo, M, d, (const int*)nullptr, (long long)vocab, sumsq));
     return BR_OK;
 }
 

@@ -199,8 +199,10 @@ class RolloutEngine:
         ssq_a = torch.zeros(32, device=dev, dtype=torch.float32)            # sum x^2 of the residual stream entering attention
         ssq_b = torch.zeros(32, device=dev, dtype=torch.float32)            # ... entering the MLP (ping-pong, see br_skinny_gemm_ex)
 
+        samp_ws = ops.sample_workspace(R, cfg.vocab_size, dev)
+
         def sample(logits):
-            ops.sample_next(logits, temperature=params.temperature, top_k=params.top_k, top_p=params.top_p, do_sample=params.do_sample,
+            ops.sample_next(logits, workspace=samp_ws, temperature=params.temperature, top_k=params.top_k, top_p=params.top_p, do_sample=params.do_sample,
                             uniforms=uniforms if params.do_sample else None, step=step, max_steps=C, eos_id=eos,
                             pad_id=params.pad_token_id if params.pad_token_id is not None else 0, finished=finished, tokens=tokens,
                             next_ids=next_ids)

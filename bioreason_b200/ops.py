@@ -308,10 +308,20 @@ def decode_attn_fused(qkv_raw, q_norm_w, k_norm_w, kcache, vcache, page_table, c
     return out
 
 
+def sample_workspace(R, V, device):
+    return torch.empty(lib().br_sample_workspace_bytes(R, V), device=device, dtype=torch.uint8)
+
+
 def sample_next(logits, *, temperature=1.0, top_k=20, top_p=1.0, do_sample=True, uniforms=None, step=None, max_steps=1,
-                eos_id=-1, pad_id=0, finished=None, tokens=None, next_ids=None):
+                eos_id=-1, pad_id=0, finished=None, tokens=None, next_ids=None, workspace=None):
     R, V = logits.shape
     assert logits.dtype == torch.float32
+    if workspace is not None and (not do_sample or top_k <= 32):
+        check(lib().br_sample_next_2stage(ptr(logits, "float*"), _row_major_2d(logits), R, V, float(temperature), int(top_k), float(top_p),
+                                          1 if do_sample else 0, ptr(uniforms, "float*"), ptr(step, "int32_t*"), int(max_steps), int(eos_id),
+                                          int(pad_id), ptr(finished, "int32_t*"), ptr(tokens, "int64_t*"), ptr(next_ids, "int64_t*"),
+                                          ptr(workspace), _stream()), "sample_next_2stage")
+        return
     check(lib().br_sample_next(ptr(logits, "float*"), _row_major_2d(logits), R, V, float(temperature), int(top_k), float(top_p),
                                1 if do_sample else 0, ptr(uniforms, "float*"), ptr(step, "int32_t*"), int(max_steps), int(eos_id),
                                int(pad_id), ptr(finished, "int32_t*"), ptr(tokens, "int64_t*"), ptr(next_ids, "int64_t*"), _stream()),

@@ -150,6 +150,12 @@ int br_decode_attn(const void* qkv, int64_t ld, const void* kcache, const void* 
 int br_sample_next(const float* logits, int64_t ld, int R, int V, float temperature, int top_k, float top_p, int do_sample,
                    const float* uniforms, const int32_t* step, int max_steps, int64_t eos_id, int64_t pad_id, int32_t* finished,
                    int64_t* tokens, int64_t* next_ids, void* stream);
+/* Same semantics in two stages for large vocabularies: stage 1 (V/4096 CTAs per row) reduces each row to <= 64 candidates
+ * per 4096-logit chunk, stage 2 samples from the candidates (top_k <= 32). */
+int64_t br_sample_workspace_bytes(int R, int V);
+int br_sample_next_2stage(const float* logits, int64_t ld, int R, int V, float temperature, int top_k, float top_p, int do_sample,
+                          const float* uniforms, const int32_t* step, int max_steps, int64_t eos_id, int64_t pad_id,
+                          int32_t* finished, int64_t* tokens, int64_t* next_ids, void* workspace, void* stream);
 int br_decode_advance(int32_t* step, int32_t* cur_len, int R, void* stream);
 
 /* Fused decode attention (one launch per layer per step): per-head q/k RMSNorm + RoPE at cur_len[r], K/V append to the

@@ -137,6 +137,11 @@ def test_sampler_matches_hf_warpers(ops):
         ops.sample_next(logits.cuda(), temperature=0.6, top_k=20, top_p=0.95, do_sample=True, uniforms=uni.cuda(), step=step, max_steps=C,
                         eos_id=-1, pad_id=0, finished=fin, tokens=tokens, next_ids=nxt)
         got = nxt.cpu()
+        # the two-stage (chunk candidates -> merge) sampler must make exactly the same choice on the same logits
+        nxt2 = torch.zeros_like(nxt); tok2 = torch.zeros_like(tokens)
+        ops.sample_next(logits.cuda(), temperature=0.6, top_k=20, top_p=0.95, do_sample=True, uniforms=uni.cuda(), step=step, max_steps=C,
+                        eos_id=-1, pad_id=0, finished=fin, tokens=tok2, next_ids=nxt2, workspace=ops.sample_workspace(R, V, "cuda"))
+        assert torch.equal(nxt2.cpu(), got)
         assert torch.all(probs.gather(1, got[:, None]) > 0)                # always inside HF's support
         mism += (got != ref).sum().item()
         assert torch.equal(tokens[:, s].cpu(), got)
@@ -147,6 +152,10 @@ def test_sampler_matches_hf_warpers(ops):
     ops.sample_next(logits.cuda(), do_sample=False, step=step, max_steps=C, eos_id=123, pad_id=999, finished=fin, tokens=tokens, next_ids=nxt)
     want = logits.argmax(-1); want[5] = 999
     assert torch.equal(nxt.cpu(), want) and fin[3].item() == 1 and fin[5].item() == 1 and fin[0].item() == 0
+    fin.zero_(); fin[5] = 1
+    ops.sample_next(logits.cuda(), do_sample=False, step=step, max_steps=C, eos_id=123, pad_id=999, finished=fin, tokens=tokens, next_ids=nxt,
+                    workspace=ops.sample_workspace(R, V, "cuda"))
+    assert torch.equal(nxt.cpu(), want) and fin[3].item() == 1
 
 
 def _first_mismatch_ok(got, want, margins, tol):
