@@ -38,8 +38,14 @@ __device__ __forceinline__ void norm_rope(const bf16* __restrict__ src, const bf
     float lo[E], hi[E], ss = 0.f;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-        lo[e] = __bfloat162float(src[lane * E + e]); hi[e] = __bfloat162float(src[D / 2 + lane * E + e]);
-        ss += lo[e] * lo[e] + hi[e] * hi[e];
+        ss += 0.f;
+    }
+    {   // E == 2: one 32-bit L2 load per half (PDL chain: no L1 for data rewritten by other kernels of the chain)
+        static_assert(E == 2, "norm_rope assumes head_dim 128");
+        const float2 a = br::unpack_bf16(__ldcg(reinterpret_cast<const unsigned int*>(src + lane * E)));
+        const float2 b = br::unpack_bf16(__ldcg(reinterpret_cast<const unsigned int*>(src + D / 2 + lane * E)));
+        lo[0] = a.x; lo[1] = a.y; hi[0] = b.x; hi[1] = b.y;
+        ss = a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
     }
     const float rstd = rsqrtf(br::warp_sum(ss) / (float)D + eps);
 #pragma unroll
@@ -87,7 +93,7 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
 
     int kv_len = 0, pg_lo, pg_hi;
     if (shared_pass) { pg_lo = split; pg_hi = n_sh; }
-    else { kv_len = p.cur_len[row_base] + 1; pg_lo = n_sh + split; pg_hi = (kv_len + 63) >> 6; }
+    else { kv_len = __ldcg(p.cur_len + row_base) + 1; pg_lo = n_sh + split; pg_hi = (kv_len + 63) >> 6; }
 
     // ---- queries: norm + rope straight into the swizzled smem tile (slot s -> row s / GQ, head kvh*GQ + s % GQ)
     for (int s = warp; s < QROWS; s += 2) {
@@ -96,7 +102,7 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
         float olo[E], ohi[E];
         if (ok) {
             const int row = row_base + rr;
-            norm_rope<D>(p.qkv + (long long)row * p.ld + (long long)hh * D, p.qw, p.cur_len[row], p.theta, p.eps, lane, olo, ohi);
+            norm_rope<D>(p.qkv + (long long)row * p.ld + (long long)hh * D, p.qw, __ldcg(p.cur_len + row), p.theta, p.eps, lane, olo, ohi);
         } else {
 #pragma unroll
             for (int e = 0; e < E; ++e) olo[e] = ohi[e] = 0.f;
@@ -122,7 +128,7 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
             } else {
                 const bf16* src = p.qkv + (long long)row_base * p.ld + (long long)(p.Hq + p.Hkv + kvh) * D;
                 bf16* dst = p.vcache + ((long long)page * p.Hkv + kvh) * 64 * D + (long long)slot * D;
-                if (lane < D / 8) reinterpret_cast<uint4*>(dst)[lane] = reinterpret_cast<const uint4*>(src)[lane];
+                if (lane < D / 8) reinterpret_cast<uint4*>(dst)[lane] = __ldcg(reinterpret_cast<const uint4*>(src) + lane);
             }
             __threadfence();
         }

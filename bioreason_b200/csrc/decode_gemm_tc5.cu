@@ -11,6 +11,9 @@
 //     small-N layers (o_proj / down_proj: 20 feature tiles) still load all 148 SMs evenly.  A tile finished by several CTAs
 //     is reduced with fp32 atomics into a scratch tile; the last arriver applies the epilogue and re-zeros the scratch.
 // Epilogues: bf16 store, +residual, SwiGLU over (8 gate | 8 up) feature blocks, fp32 logits.
+// PDL: the kernel is launched with programmatic stream serialization.  Kernels chained this way are NOT separated by the
+// usual launch-boundary L1 invalidation, so every load of data another kernel of the chain rewrites (residual, statistics,
+// scratch) goes through L2 (ld.global.cg / TMA), never through L1.
 #include "br_common.cuh"
 #include "../../include/bioreason_b200.h"
 
@@ -58,7 +61,7 @@ __device__ __forceinline__ void apply_epilogue(const SkParams& p, int f, int lan
     const bool f_ok = f < p.N;
     float rs[BNX];
 #pragma unroll
-    for (int r = 0; r < BNX; ++r) rs[r] = (p.sumsq_in && r < p.R) ? rsqrtf(__ldg(p.sumsq_in + r) / (float)p.K + p.eps) : 1.f;
+    for (int r = 0; r < BNX; ++r) rs[r] = (p.sumsq_in && r < p.R) ? rsqrtf(__ldcg(p.sumsq_in + r) / (float)p.K + p.eps) : 1.f;   // L2 load: see note on PDL below
     if (p.mode == 2) {
         // lanes 0-7 / 16-23 hold gate features, 8-15 / 24-31 the matching up features (blocks of 16 features)
 #pragma unroll
@@ -80,7 +83,7 @@ __device__ __forceinline__ void apply_epilogue(const SkParams& p, int f, int lan
         if (f_ok) {
             if (p.mode == 3) reinterpret_cast<float*>(p.out)[(long long)r * p.ldo + f] = x;
             else {
-                if (p.mode == 1) x = rbf(x) + __bfloat162float(p.res[(long long)r * p.ldr + f]);
+                if (p.mode == 1) x = rbf(x) + __bfloat162float(__ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(p.res) + (long long)r * p.ldr + f)));
                 const bf16 xb = __float2bfloat16(x);
                 reinterpret_cast<bf16*>(p.out)[(long long)r * p.ldo + f] = xb;
                 sq = __bfloat162float(xb) * __bfloat162float(xb);

@@ -169,7 +169,7 @@ __global__ void embed_gather_kernel(const long long* __restrict__ ids, const bf1
     br::launch_dependents();
     br::grid_dep_wait();
     if (row >= M) return;
-    long long id = ids[row];
+    long long id = __ldcg(ids + row);
     const bool zero = (keep && keep[row] == 0) || id < 0 || id >= vocab;
     const uint4* src = reinterpret_cast<const uint4*>(table + (zero ? 0 : id) * ldt);
     uint4* dst = reinterpret_cast<uint4*>(out + (long long)row * ldo);

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) sampler_partial_kernel(const float* __res
     for (int i = 0; i < 16; ++i) {
         const int idx = base + i * 256 + tid;
         const bool ok = idx < V;
-        v[i] = ok ? x[idx] : -INFINITY;
+        v[i] = ok ? __ldcg(x + idx) : -INFINITY;          // L2 loads throughout: PDL-chained kernels keep no coherent L1
         key[i] = ok ? fkey(v[i]) : 0u;
         n_valid += ok;
     }
@@ -140,13 +140,13 @@ __global__ void __launch_bounds__(1024) sampler_kernel(const float* __restrict__
     br::grid_dep_wait();
     const float* x = logits + (long long)row * ld;
     const int* xi = cand_idx_all ? cand_idx_all + (long long)row * ld : nullptr;
-    auto IDX = [&](int i) { return xi ? xi[i] : i; };
-    const int step = step_ptr ? *step_ptr : 0;
+    auto IDX = [&](int i) { return xi ? __ldcg(xi + i) : i; };
+    const int step = step_ptr ? __ldcg(step_ptr) : 0;
     long long choice;
 
     if (!do_sample) {
         float bv = -INFINITY; int bi = 0x7fffffff;
-        for (int i = tid; i < V; i += blockDim.x) { float v = x[i]; const int id = IDX(i); if (v > bv || (v == bv && id < bi)) { bv = v; bi = id; } }
+        for (int i = tid; i < V; i += blockDim.x) { float v = __ldcg(x + i); const int id = IDX(i); if (v > bv || (v == bv && id < bi)) { bv = v; bi = id; } }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             float ov = __shfl_xor_sync(0xffffffffu, bv, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(1024) sampler_kernel(const float* __restrict__
             for (int i = tid; i < 2048; i += blockDim.x) hist[i] = 0;
             __syncthreads();
             for (int i = tid; i < V; i += blockDim.x) {
-                const uint32_t k = fkey(x[i]);
+                const uint32_t k = fkey(__ldcg(x + i));
                 bool in;
                 if (pass == 0) in = true; else if (pass == 1) in = (k >> 21) == prefix; else in = (k >> 10) == prefix;
                 if (in) atomicAdd(&hist[(k >> shift) & (nb - 1)], 1);
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(1024) sampler_kernel(const float* __restrict__
         if (tid == 0) s_count = 0;
         __syncthreads();
         for (int i = tid; i < V; i += blockDim.x) {
-            const float v = x[i];
+            const float v = __ldcg(x + i);
             if (fkey(v) >= thr && v > -INFINITY) {
                 const int s = atomicAdd(&s_count, 1);
                 if (s < MAXC) { c_val[s] = v; c_idx[s] = IDX(i); }
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(1024) sampler_kernel(const float* __restrict__
         choice = s_tmp[2];
     }
     if (tid == 0) {
-        const int fin = finished ? finished[row] : 0;
+        const int fin = finished ? __ldcg(finished + row) : 0;
         long long tok = fin ? pad_id : choice;                         // finished rows emit pad (HF :2796-2797)
         if (tokens && step < max_steps) tokens[(long long)row * max_steps + step] = tok;
         if (next_ids) next_ids[row] = tok;
@@ -258,8 +258,8 @@ __global__ void advance_kernel(int* step, int* cur_len, int R) {
     const int i = threadIdx.x;
     br::launch_dependents();
     br::grid_dep_wait();
-    if (i < R) cur_len[i] += 1;
-    if (i == 0 && step) *step += 1;
+    if (i < R) atomicAdd(cur_len + i, 1);
+    if (i == 0 && step) atomicAdd(step, 1);
 }
 
 }  // namespace

@@ -5,6 +5,7 @@ are not CUDA tensors -- there is no CPU path.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -316,7 +317,7 @@ def sample_next(logits, *, temperature=1.0, top_k=20, top_p=1.0, do_sample=True,
                 eos_id=-1, pad_id=0, finished=None, tokens=None, next_ids=None, workspace=None):
     R, V = logits.shape
     assert logits.dtype == torch.float32
-    if workspace is not None and (not do_sample or top_k <= 32):
+    if workspace is not None and (not do_sample or top_k <= 32) and not os.environ.get("BR_SAMPLER_1STAGE"):
         check(lib().br_sample_next_2stage(ptr(logits, "float*"), _row_major_2d(logits), R, V, float(temperature), int(top_k), float(top_p),
                                           1 if do_sample else 0, ptr(uniforms, "float*"), ptr(step, "int32_t*"), int(max_steps), int(eos_id),
                                           int(pad_id), ptr(finished, "int32_t*"), ptr(tokens, "int64_t*"), ptr(next_ids, "int64_t*"),

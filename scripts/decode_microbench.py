@@ -93,3 +93,21 @@ us = timed_graph(lambda: ops.decode_advance(step, cur), inner=4)
 print(f"decode_advance: {us:8.2f} us")
 tot = 36 * (res["qkv"][0] + res["o"][0] + res["gate_up"][0] + res["down"][0] + res["attn_fused_8_2"][0]) + res["lm_head"][0]
 print(f"estimated token step (36 layers): {tot / 1e3:.3f} ms")
+
+# ---- a real layer chain (qkv -> fused attention -> o -> gate/up -> down) x NL in one graph: what a token step actually costs
+ws_l = [dict(qkv=torch.randn((Hq + 2 * Hkv) * D, d, device=dev).to(bf) * 0.02, o=torch.randn(d, Hq * D, device=dev).to(bf) * 0.02,
+             gu=torch.randn(2 * F, d, device=dev).to(bf) * 0.02, down=torch.randn(d, F, device=dev).to(bf) * 0.02) for _ in range(NL)]
+x0 = torch.randn(R, d, device=dev).to(bf)
+ssa = torch.ones(32, device=dev); ssb = torch.ones(32, device=dev)
+wsf = ops.decode_fused_workspace(R, Hq, Hkv, D, 10, dev)
+attn_out = torch.empty(R, Hq * D, device=dev, dtype=bf)
+def chain():
+    x = x0
+    for w in ws_l:
+        q = ops.skinny_gemm(x, w["qkv"], scratch, sumsq_in=ssa, eps=1e-6)
+        ops.decode_attn_fused(q, qn, kn, kc, vc, table, cur, G, Hq, Hkv, D, n_shared, 8, 2, 1e6, 1e-6, wsf, attn_out)
+        x2 = ops.skinny_gemm(attn_out, w["o"], scratch, mode=1, residual=x, sumsq_out=ssb, zero_buf=ssa)
+        a = ops.skinny_gemm(x2, w["gu"], scratch, mode=2, sumsq_in=ssb, eps=1e-6)
+        x = ops.skinny_gemm(a, w["down"], scratch, mode=1, residual=x2, sumsq_out=ssa, zero_buf=ssb)
+us = timed_graph(chain) / NL
+print(f"layer chain (5 launches): {us:8.2f} us per layer  -> {36 * us / 1e3:.3f} ms per token (36 layers)   PDL={'off' if os.environ.get('BR_NO_PDL') else 'on'}")
