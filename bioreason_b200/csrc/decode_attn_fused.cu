@@ -28,12 +28,25 @@ struct FusedParams {
     float* part_o; float* part_lse; int* counters;      // [R,Hq,n_slots,D], [R,Hq,n_slots], [R*Hkv]
     bf16* out; long long ldo;
     float scale_log2, theta, eps;
+    const float2* rope;                  // [n_pos, D/2] (cos, sin), bf16-rounded like HF's tables; may be null (computed inline)
+    int rope_n_pos;
 };
+
+// cos/sin table: rope[pos, j] = (bf16(cos(pos * theta^(-2j/D))), bf16(sin(...))) -- the transcendental work of the decode loop, done once
+__global__ void rope_table_kernel(float2* __restrict__ out, int n_pos, int half, float theta) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pos * half) return;
+    const int pos = i / half, j = i % half;
+    const float inv_freq = 1.0f / powf(theta, (float)(2 * j) / (float)(2 * half));
+    float sn, cs;
+    sincosf((float)pos * inv_freq, &sn, &cs);
+    out[i] = make_float2(rbf(cs), rbf(sn));
+}
 
 // norm + rope of one 128-wide head vector held as (lo[2], hi[2]) per lane; returns roped values
 template <int D>
 __device__ __forceinline__ void norm_rope(const bf16* __restrict__ src, const bf16* __restrict__ w, int pos, float theta, float eps, int lane,
-                                          float (&olo)[D / 64], float (&ohi)[D / 64]) {
+                                          float (&olo)[D / 64], float (&ohi)[D / 64], const float2* __restrict__ rope, int rope_n_pos) {
     constexpr int E = D / 64;
     float lo[E], hi[E], ss = 0.f;
 #pragma unroll
@@ -53,10 +66,15 @@ __device__ __forceinline__ void norm_rope(const bf16* __restrict__ src, const bf
         const int j = lane * E + e;
         const float a = rbf(__bfloat162float(w[j]) * rbf(lo[e] * rstd));
         const float b = rbf(__bfloat162float(w[D / 2 + j]) * rbf(hi[e] * rstd));
-        const float inv_freq = 1.0f / powf(theta, (float)(2 * j) / (float)D);
         float sn, cs;
-        sincosf((float)pos * inv_freq, &sn, &cs);
-        sn = rbf(sn); cs = rbf(cs);
+        if (rope && pos < rope_n_pos) {                       // table built once per rollout by br_rope_table (same arithmetic)
+            const float2 t = __ldg(rope + (long long)pos * (D / 2) + j);
+            cs = t.x; sn = t.y;
+        } else {
+            const float inv_freq = 1.0f / powf(theta, (float)(2 * j) / (float)D);
+            sincosf((float)pos * inv_freq, &sn, &cs);
+            sn = rbf(sn); cs = rbf(cs);
+        }
         olo[e] = rbf(a * cs) + rbf(-b * sn);
         ohi[e] = rbf(b * cs) + rbf(a * sn);
     }
@@ -102,7 +120,7 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
         float olo[E], ohi[E];
         if (ok) {
             const int row = row_base + rr;
-            norm_rope<D>(p.qkv + (long long)row * p.ld + (long long)hh * D, p.qw, __ldcg(p.cur_len + row), p.theta, p.eps, lane, olo, ohi);
+            norm_rope<D>(p.qkv + (long long)row * p.ld + (long long)hh * D, p.qw, __ldcg(p.cur_len + row), p.theta, p.eps, lane, olo, ohi, p.rope, p.rope_n_pos);
         } else {
 #pragma unroll
             for (int e = 0; e < E; ++e) olo[e] = ohi[e] = 0.f;
@@ -120,7 +138,7 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
             const int page = table[last_pg], slot = pos & 63;
             if (warp == 0) {
                 float olo[E], ohi[E];
-                norm_rope<D>(p.qkv + (long long)row_base * p.ld + (long long)(p.Hq + kvh) * D, p.kw, pos, p.theta, p.eps, lane, olo, ohi);
+                norm_rope<D>(p.qkv + (long long)row_base * p.ld + (long long)(p.Hq + kvh) * D, p.kw, pos, p.theta, p.eps, lane, olo, ohi, p.rope, p.rope_n_pos);
                 bf16* dst = p.kcache + ((long long)page * p.Hkv + kvh) * 64 * D + (long long)slot * D;
                 const int j0 = lane * E;
                 *reinterpret_cast<uint32_t*>(dst + j0) = br::pack_bf16(olo[0], olo[1]);
@@ -300,10 +318,18 @@ int64_t br_decode_fused_workspace_bytes(int R, int n_q_heads, int n_kv_heads, in
     return (int64_t)R * n_q_heads * n_slots * (head_dim + 1) * sizeof(float) + (int64_t)R * n_kv_heads * sizeof(int);
 }
 
+int br_rope_table(float* out, int n_pos, int head_dim, float theta, void* stream) {
+    BR_CHECK_ARG(n_pos > 0 && head_dim % 2 == 0, "rope_table: bad shape");
+    const int n = n_pos * (head_dim / 2);
+    rope_table_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((float2*)out, n_pos, head_dim / 2, theta);
+    BR_CHECK_LAUNCH();
+    return BR_OK;
+}
+
 int br_decode_attn_fused(const void* qkv_raw, int64_t ld, const void* q_norm_w, const void* k_norm_w, void* kcache, void* vcache,
                          const int32_t* page_table, int max_pages, const int32_t* cur_len, int R, int G, int n_q_heads, int n_kv_heads,
                          int head_dim, int n_shared_pages, int splits_shared, int splits_private, float scale, float theta, float eps,
-                         void* workspace, void* out, int64_t ldo, void* stream) {
+                         const float* rope_table, int rope_n_pos, void* workspace, void* out, int64_t ldo, void* stream) {
     BR_CHECK_ARG(head_dim == 128, "decode_attn_fused: head_dim 128 only");
     BR_CHECK_ARG(R > 0 && G > 0 && R % G == 0 && G <= 64, "decode_attn_fused: R=%d must be a multiple of G=%d (<= 64)", R, G);
     const int GQ = n_q_heads / n_kv_heads;
@@ -321,6 +347,7 @@ int br_decode_attn_fused(const void* qkv_raw, int64_t ld, const void* q_norm_w, 
     p.part_lse = p.part_o + (int64_t)R * n_q_heads * p.n_slots * D;
     p.counters = (int*)(p.part_lse + (int64_t)R * n_q_heads * p.n_slots);
     p.out = (bf16*)out; p.ldo = ldo; p.scale_log2 = scale * 1.4426950408889634f; p.theta = theta; p.eps = eps;
+    p.rope = (const float2*)rope_table; p.rope_n_pos = rope_table ? rope_n_pos : 0;
     constexpr int SMEM = 32 * D * 2 + 4 * 64 * D * 2;
     static bool done = false;
     if (!done) { BR_CHECK_CUDA(cudaFuncSetAttribute(decode_fused_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); done = true; }

@@ -195,6 +195,7 @@ class RolloutEngine:
         n_slots = splits_shared + splits_private
         ws = ops.decode_fused_workspace(R, Hq, Hkv, D, n_slots, dev)
         attn_out = torch.empty(R, Hq * D, device=dev, dtype=torch.bfloat16)
+        rope = ops.rope_table(max(plen) + C + 1, D, theta, dev)
         h = torch.empty(R, d, device=dev, dtype=torch.bfloat16)
         ssq_a = torch.zeros(32, device=dev, dtype=torch.float32)            # sum x^2 of the residual stream entering attention
         ssq_b = torch.zeros(32, device=dev, dtype=torch.float32)            # ... entering the MLP (ping-pong, see br_skinny_gemm_ex)
@@ -222,7 +223,7 @@ class RolloutEngine:
             for li, Lw in enumerate(Wd.layers):
                 qkv = ops.skinny_gemm(x, Lw.w_qkv, scratch, sumsq_in=ssq_a, eps=eps)
                 ops.decode_attn_fused(qkv, Lw.q_norm, Lw.k_norm, kc[li], vc[li], table, cur_len, G, Hq, Hkv, D, n_shared, splits_shared,
-                                      splits_private, theta, eps, ws, attn_out)
+                                      splits_private, theta, eps, ws, attn_out, rope=rope)
                 x2 = ops.skinny_gemm(attn_out, Lw.w_o, scratch, mode=1, residual=x, sumsq_out=ssq_b, zero_buf=ssq_a)
                 act = ops.skinny_gemm(x2, Lw.w_gu, scratch, mode=2, sumsq_in=ssq_b, eps=eps)
                 x = ops.skinny_gemm(act, Lw.w_down, scratch, mode=1, residual=x2, sumsq_out=ssq_a, zero_buf=ssq_b)

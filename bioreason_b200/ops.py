@@ -297,14 +297,21 @@ def decode_fused_workspace(R, n_q, n_kv, head_dim, n_slots, device):
     return torch.zeros(lib().br_decode_fused_workspace_bytes(R, n_q, n_kv, head_dim, n_slots), device=device, dtype=torch.uint8)
 
 
+def rope_table(n_pos, head_dim, theta, device):
+    t = torch.empty(n_pos, head_dim // 2, 2, device=device, dtype=torch.float32)
+    check(lib().br_rope_table(ptr(t, "float*"), n_pos, head_dim, float(theta), _stream()), "rope_table")
+    return t
+
+
 def decode_attn_fused(qkv_raw, q_norm_w, k_norm_w, kcache, vcache, page_table, cur_len, G, n_q, n_kv, head_dim, n_shared_pages,
-                      splits_shared, splits_private, theta, eps, workspace, out, scale=None):
+                      splits_shared, splits_private, theta, eps, workspace, out, scale=None, rope=None):
     R = qkv_raw.shape[0]
     if scale is None:
         scale = head_dim ** -0.5
     check(lib().br_decode_attn_fused(ptr(qkv_raw), _row_major_2d(qkv_raw), ptr(q_norm_w), ptr(k_norm_w), ptr(kcache), ptr(vcache),
                                      ptr(page_table, "int32_t*"), page_table.shape[1], ptr(cur_len, "int32_t*"), R, G, n_q, n_kv,
                                      head_dim, n_shared_pages, splits_shared, splits_private, float(scale), float(theta), float(eps),
+                                     ptr(rope, "float*"), rope.shape[0] if rope is not None else 0,
                                      ptr(workspace), ptr(out), _row_major_2d(out), _stream()), "decode_attn_fused")
     return out
 

@@ -165,7 +165,11 @@ int64_t br_decode_fused_workspace_bytes(int R, int n_q_heads, int n_kv_heads, in
 int br_decode_attn_fused(const void* qkv_raw, int64_t ld, const void* q_norm_w, const void* k_norm_w, void* kcache, void* vcache,
                          const int32_t* page_table, int max_pages, const int32_t* cur_len, int R, int G, int n_q_heads,
                          int n_kv_heads, int head_dim, int n_shared_pages, int splits_shared, int splits_private, float scale,
-                         float theta, float eps, void* workspace, void* out, int64_t ldo, void* stream);
+                         float theta, float eps, const float* rope_table, int rope_n_pos, void* workspace, void* out, int64_t ldo,
+                         void* stream);
+/* rope_table [n_pos, head_dim/2, 2] f32 = (cos, sin) rounded to bf16 precision (HF builds its tables in the model dtype);
+ * optional input of br_decode_attn_fused: removes powf/sincosf from the decode loop. */
+int br_rope_table(float* out, int n_pos, int head_dim, float theta, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Backward (autograd counterparts; frozen base weights + LoRA adapters, reason.py:362-394)

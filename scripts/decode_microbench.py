@@ -67,10 +67,11 @@ kc = torch.randn(n_pages, Hkv, PAGE, D, device=dev).to(bf); vc = torch.randn_lik
 qkv = torch.randn(R, (Hq + 2 * Hkv) * D, device=dev).to(bf)
 qn = torch.ones(D, device=dev).to(bf); kn = torch.ones(D, device=dev).to(bf)
 cur = torch.full((R,), T, dtype=torch.int32, device=dev)
-for ss, sp in ((8, 2), (16, 2), (8, 4)):
+rope = ops.rope_table(T + 8, D, 1e6, dev)
+for ss, sp in ((8, 2), (16, 2), (8, 4), (4, 1)):
     wsf = ops.decode_fused_workspace(R, Hq, Hkv, D, ss + sp, dev)
     out = torch.empty(R, Hq * D, device=dev, dtype=bf)
-    us = timed_graph(lambda: ops.decode_attn_fused(qkv, qn, kn, kc, vc, table, cur, G, Hq, Hkv, D, n_shared, ss, sp, 1e6, 1e-6, wsf, out), inner=4)
+    us = timed_graph(lambda: ops.decode_attn_fused(qkv, qn, kn, kc, vc, table, cur, G, Hq, Hkv, D, n_shared, ss, sp, 1e6, 1e-6, wsf, out, rope=rope), inner=4)
     print(f"decode_attn_fused ctx={T} splits=({ss},{sp}): {us:8.2f} us")
     res[f"attn_fused_{ss}_{sp}"] = (us, 0)
 
@@ -98,6 +99,7 @@ print(f"estimated token step (36 layers): {tot / 1e3:.3f} ms")
 ws_l = [dict(qkv=torch.randn((Hq + 2 * Hkv) * D, d, device=dev).to(bf) * 0.02, o=torch.randn(d, Hq * D, device=dev).to(bf) * 0.02,
              gu=torch.randn(2 * F, d, device=dev).to(bf) * 0.02, down=torch.randn(d, F, device=dev).to(bf) * 0.02) for _ in range(NL)]
 x0 = torch.randn(R, d, device=dev).to(bf)
+cur.fill_(T); step.zero_()          # decode_advance above moved them
 ssa = torch.ones(32, device=dev); ssb = torch.ones(32, device=dev)
 wsf = ops.decode_fused_workspace(R, Hq, Hkv, D, 10, dev)
 attn_out = torch.empty(R, Hq * D, device=dev, dtype=bf)
@@ -105,7 +107,7 @@ def chain():
     x = x0
     for w in ws_l:
         q = ops.skinny_gemm(x, w["qkv"], scratch, sumsq_in=ssa, eps=1e-6)
-        ops.decode_attn_fused(q, qn, kn, kc, vc, table, cur, G, Hq, Hkv, D, n_shared, 8, 2, 1e6, 1e-6, wsf, attn_out)
+        ops.decode_attn_fused(q, qn, kn, kc, vc, table, cur, G, Hq, Hkv, D, n_shared, 8, 2, 1e6, 1e-6, wsf, attn_out, rope=rope)
         x2 = ops.skinny_gemm(attn_out, w["o"], scratch, mode=1, residual=x, sumsq_out=ssb, zero_buf=ssa)
         a = ops.skinny_gemm(x2, w["gu"], scratch, mode=2, sumsq_in=ssb, eps=1e-6)
         x = ops.skinny_gemm(a, w["down"], scratch, mode=1, residual=x2, sumsq_out=ssa, zero_buf=ssb)

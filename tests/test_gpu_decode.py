@@ -106,8 +106,10 @@ def test_decode_attention_paged_prefix_shared(ops, U, G, Hq, Hkv, plen, gen):
             kc2[pg, :, T % PAGE] = 0; vc2[pg, :, T % PAGE] = 0
         wsf = ops.decode_fused_workspace(R, Hq, Hkv, D, ss + sp, "cuda")
         out2 = torch.empty_like(out)
-        for _ in range(2):                                                 # twice: arrival counters must self-reset
-            ops.decode_attn_fused(raw_qkv, qn, kn, kc2, vc2, table, cur, G, Hq, Hkv, D, n_shared, ss, sp, 1e6, 1e-6, wsf, out2)
+        rope = ops.rope_table(T + 2, D, 1e6, "cuda")
+        for it in range(3):                                                # repeated: arrival counters must self-reset; with/without table
+            ops.decode_attn_fused(raw_qkv, qn, kn, kc2, vc2, table, cur, G, Hq, Hkv, D, n_shared, ss, sp, 1e6, 1e-6, wsf, out2,
+                                  rope=rope if it else None)
             torch.testing.assert_close(out2.float(), ref, rtol=2e-2, atol=2e-2)
         assert torch.equal(kc2, kc) and torch.equal(vc2, vc)
 
