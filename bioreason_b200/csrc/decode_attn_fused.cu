@@ -45,21 +45,13 @@ __global__ void rope_table_kernel(float2* __restrict__ out, int n_pos, int half,
 
 // norm + rope of one 128-wide head vector held as (lo[2], hi[2]) per lane; returns roped values
 template <int D>
-__device__ __forceinline__ void norm_rope(const bf16* __restrict__ src, const bf16* __restrict__ w, int pos, float theta, float eps, int lane,
-                                          float (&olo)[D / 64], float (&ohi)[D / 64], const float2* __restrict__ rope, int rope_n_pos) {
+__device__ __forceinline__ void norm_rope_words(uint32_t wlo, uint32_t whi, const bf16* __restrict__ w, int pos, float theta, float eps, int lane,
+                                                float (&olo)[D / 64], float (&ohi)[D / 64], const float2* __restrict__ rope, int rope_n_pos) {
     constexpr int E = D / 64;
-    float lo[E], hi[E], ss = 0.f;
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        ss += 0.f;
-    }
-    {   // E == 2: one 32-bit L2 load per half (PDL chain: no L1 for data rewritten by other kernels of the chain)
-        static_assert(E == 2, "norm_rope assumes head_dim 128");
-        const float2 a = br::unpack_bf16(__ldcg(reinterpret_cast<const unsigned int*>(src + lane * E)));
-        const float2 b = br::unpack_bf16(__ldcg(reinterpret_cast<const unsigned int*>(src + D / 2 + lane * E)));
-        lo[0] = a.x; lo[1] = a.y; hi[0] = b.x; hi[1] = b.y;
-        ss = a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
-    }
+    static_assert(E == 2, "head_dim 128");
+    const float2 a2 = br::unpack_bf16(wlo), b2 = br::unpack_bf16(whi);
+    const float lo[E] = {a2.x, a2.y}, hi[E] = {b2.x, b2.y};
+    const float ss = a2.x * a2.x + a2.y * a2.y + b2.x * b2.x + b2.y * b2.y;
     const float rstd = rsqrtf(br::warp_sum(ss) / (float)D + eps);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
@@ -78,6 +70,12 @@ __device__ __forceinline__ void norm_rope(const bf16* __restrict__ src, const bf
         olo[e] = rbf(a * cs) + rbf(-b * sn);
         ohi[e] = rbf(b * cs) + rbf(a * sn);
     }
+}
+
+// L2 loads of the two 32-bit words a lane owns of a 128-wide bf16 head vector (PDL chain: never through L1)
+__device__ __forceinline__ void load_head_words(const bf16* src, int lane, uint32_t& wlo, uint32_t& whi) {
+    wlo = __ldcg(reinterpret_cast<const unsigned int*>(src + lane * 2));
+    whi = __ldcg(reinterpret_cast<const unsigned int*>(src + 64 + lane * 2));
 }
 
 template <int D>
@@ -114,21 +112,34 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
     else { kv_len = __ldcg(p.cur_len + row_base) + 1; pg_lo = n_sh + split; pg_hi = (kv_len + 63) >> 6; }
 
     // ---- queries: norm + rope straight into the swizzled smem tile (slot s -> row s / GQ, head kvh*GQ + s % GQ)
-    for (int s = warp; s < QROWS; s += 2) {
-        const int rr = s / p.GQ, hh = kvh * p.GQ + s % p.GQ;
-        const bool ok = rr < rows_per_unit && (row_base + rr) < p.R;
-        float olo[E], ohi[E];
-        if (ok) {
-            const int row = row_base + rr;
-            norm_rope<D>(p.qkv + (long long)row * p.ld + (long long)hh * D, p.qw, __ldcg(p.cur_len + row), p.theta, p.eps, lane, olo, ohi, p.rope, p.rope_n_pos);
-        } else {
+    {
+        constexpr int NS = QROWS / 2;                        // slots per warp
+        uint32_t wlo[NS], whi[NS]; int posv[NS];
 #pragma unroll
-            for (int e = 0; e < E; ++e) olo[e] = ohi[e] = 0.f;
+        for (int i = 0; i < NS; ++i) {                        // all loads in flight before any of them is consumed
+            const int s = warp + 2 * i;
+            const int rr = s / p.GQ, hh = kvh * p.GQ + s % p.GQ;
+            const bool ok = rr < rows_per_unit && (row_base + rr) < p.R;
+            wlo[i] = whi[i] = 0u; posv[i] = -1;
+            if (ok) {
+                const int row = row_base + rr;
+                load_head_words(p.qkv + (long long)row * p.ld + (long long)hh * D, lane, wlo[i], whi[i]);
+                posv[i] = __ldcg(p.cur_len + row);
+            }
         }
-        // element j = lane*E + e lives in 16-byte chunk j / 8
-        const int j0 = lane * E;
-        *reinterpret_cast<uint32_t*>(tile_ptr<D>(sQ, s, j0 >> 3) + (j0 & 7) * 2) = br::pack_bf16(olo[0], olo[1]);
-        *reinterpret_cast<uint32_t*>(tile_ptr<D>(sQ, s, (D / 2 + j0) >> 3) + (j0 & 7) * 2) = br::pack_bf16(ohi[0], ohi[1]);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            const int s = warp + 2 * i;
+            float olo[E], ohi[E];
+            if (posv[i] >= 0) norm_rope_words<D>(wlo[i], whi[i], p.qw, posv[i], p.theta, p.eps, lane, olo, ohi, p.rope, p.rope_n_pos);
+            else {
+#pragma unroll
+                for (int e = 0; e < E; ++e) olo[e] = ohi[e] = 0.f;
+            }
+            const int j0 = lane * E;
+            *reinterpret_cast<uint32_t*>(tile_ptr<D>(sQ, s, j0 >> 3) + (j0 & 7) * 2) = br::pack_bf16(olo[0], olo[1]);
+            *reinterpret_cast<uint32_t*>(tile_ptr<D>(sQ, s, (D / 2 + j0) >> 3) + (j0 & 7) * 2) = br::pack_bf16(ohi[0], ohi[1]);
+        }
     }
     // ---- append the new token's K / V (private item that owns the newest page)
     if (!shared_pass) {
@@ -138,7 +149,9 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
             const int page = table[last_pg], slot = pos & 63;
             if (warp == 0) {
                 float olo[E], ohi[E];
-                norm_rope<D>(p.qkv + (long long)row_base * p.ld + (long long)(p.Hq + kvh) * D, p.kw, pos, p.theta, p.eps, lane, olo, ohi, p.rope, p.rope_n_pos);
+                uint32_t kwlo, kwhi;
+                load_head_words(p.qkv + (long long)row_base * p.ld + (long long)(p.Hq + kvh) * D, lane, kwlo, kwhi);
+                norm_rope_words<D>(kwlo, kwhi, p.kw, pos, p.theta, p.eps, lane, olo, ohi, p.rope, p.rope_n_pos);
                 bf16* dst = p.kcache + ((long long)page * p.Hkv + kvh) * 64 * D + (long long)slot * D;
                 const int j0 = lane * E;
                 *reinterpret_cast<uint32_t*>(dst + j0) = br::pack_bf16(olo[0], olo[1]);

@@ -27,11 +27,12 @@ struct SkParams {
     int mode;                           // 0 bf16, 1 bf16 + residual, 2 SwiGLU blocks, 3 fp32
     void* out; long long ldo;
     const bf16* res; long long ldr;
-    float* scratch;                     // [32, N] fp32 (zero between launches)
-    int* counters;                      // [tiles_n]
-    // folded RMSNorm (decode): out[r, :] *= rsqrt(sumsq_in[r] / K + eps) (the norm weight is pre-multiplied into W's columns);
-    // sumsq_out[r] += sum_f out[r, f]^2 over the bf16-rounded outputs (feeds the NEXT folded norm); zero_buf[0..32) = 0.
-    const float* sumsq_in; float* sumsq_out; float* zero_buf; float eps;
+    float* scratch;                     // [grid, 2, BNX, 128] fp32 partial tiles (slot 0: CTA's first tile, 1: its last tile)
+    int* counters;                      // [tiles_n], zero between launches (self-resetting)
+    // folded RMSNorm (decode): out[r, :] *= rsqrt(sum_i sumsq_in[i, r] / K + eps) (the norm weight is pre-multiplied into W's
+    // columns); sumsq_out[(tile*4 + warp), r] = sum over that warp's 32 features of out[r, f]^2 (bf16-rounded) -- partials are
+    // written, never accumulated with atomics, and summed in a fixed order by the consumer: the rollout is reproducible.
+    const float* sumsq_in; int sumsq_in_n; float* sumsq_out; float eps;
 };
 
 __device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16(x)); }
@@ -52,16 +53,16 @@ struct SL {
     static constexpr int STAGE = A_BYTES + B_BYTES;
     static constexpr int NSTAGE = 6;        // 108 KB: two CTAs (this kernel + its PDL successor) fit one SM
     static constexpr int TILE_BYTES = NSTAGE * STAGE;
-    static constexpr int TOTAL = TILE_BYTES + 256 + 1024;
+    static constexpr int TOTAL = TILE_BYTES + 512 + 1024;   // + barriers / flags / per-row rstd + alignment slack
 };
 
 // per-feature epilogue: v[r] = sum for row r of feature f
 template <int BNX>
-__device__ __forceinline__ void apply_epilogue(const SkParams& p, int f, int lane, const float (&v)[BNX]) {
+__device__ __forceinline__ void apply_epilogue(const SkParams& p, int f, int lane, const float (&v)[BNX], const float* s_rs, int part_row) {
     const bool f_ok = f < p.N;
     float rs[BNX];
 #pragma unroll
-    for (int r = 0; r < BNX; ++r) rs[r] = (p.sumsq_in && r < p.R) ? rsqrtf(__ldcg(p.sumsq_in + r) / (float)p.K + p.eps) : 1.f;   // L2 load: see note on PDL below
+    for (int r = 0; r < BNX; ++r) rs[r] = s_rs[r];
     if (p.mode == 2) {
         // lanes 0-7 / 16-23 hold gate features, 8-15 / 24-31 the matching up features (blocks of 16 features)
 #pragma unroll
@@ -91,7 +92,7 @@ __device__ __forceinline__ void apply_epilogue(const SkParams& p, int f, int lan
         }
         if (p.sumsq_out) {
             sq = br::warp_sum(sq);
-            if (lane == 0) atomicAdd(p.sumsq_out + r, sq);
+            if (lane == 0) p.sumsq_out[(long long)part_row * 32 + r] = sq;
         }
     }
 }
@@ -108,6 +109,7 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
+    float* s_rs = reinterpret_cast<float*>(s_flag + 1);       // [32] per-row rstd of the folded RMSNorm
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int u_lo = blockIdx.x * p.chunk;
@@ -186,7 +188,16 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         const int lane_grp = warp & 3;
         const int et = threadIdx.x - 64;                      // 0..127 within the epilogue group
         br::grid_dep_wait();                                  // everything below touches data shared with earlier kernels
-        if (p.zero_buf && blockIdx.x == 0 && et < 32) p.zero_buf[et] = 0.f;
+        if (et < 32) {                                        // fixed-order sum of the producer's partial statistics
+            float rsv = 1.f;
+            if (p.sumsq_in && et < p.R) {
+                float acc = 0.f;
+                for (int i = 0; i < p.sumsq_in_n; ++i) acc += __ldcg(p.sumsq_in + (long long)i * 32 + et);
+                rsv = rsqrtf(acc / (float)p.K + p.eps);
+            }
+            s_rs[et] = rsv;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         int as = 0; uint32_t aph = 0;
         int u = u_lo;
         while (u < u_hi) {
@@ -211,31 +222,35 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             if (lane == 0) br::mbar_arrive(&tempty_bar[as]);   // accumulator drained into registers
             if (++as == 2) { as = 0; aph ^= 1; }
             const int f = tile * BM + lane_grp * 32 + lane;
+            const int part_row = tile * 4 + lane_grp;
             if (whole) {
-                apply_epilogue<BNX>(p, f, lane, v);
+                apply_epilogue<BNX>(p, f, lane, v, s_rs, part_row);
             } else {
-                if (f < p.N) {
+                // deterministic stream-K: write this CTA's partial tile to its own scratch slot; the last arriver adds the
+                // partials of the contributing CTAs in ascending CTA order (no floating-point atomics anywhere)
+                const int first_c = (tile * p.KB) / p.chunk, last_c = ((tile + 1) * p.KB - 1) / p.chunk;
+                const int my_slot = (tile == u_lo / p.KB) ? 0 : 1;
+                float* mine = p.scratch + (((long long)blockIdx.x * 2 + my_slot) * BNX) * BM + lane_grp * 32 + lane;
 #pragma unroll
-                    for (int r = 0; r < BNX; ++r)
-                        if (r < p.R) atomicAdd(p.scratch + (long long)r * p.N + f, v[r]);
-                }
+                for (int r = 0; r < BNX; ++r)
+                    if (r < p.R) __stcg(mine + r * BM, v[r]);
                 __threadfence();
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (et == 0) {
-                    const int first = (tile * p.KB) / p.chunk, last = ((tile + 1) * p.KB - 1) / p.chunk;
-                    *s_flag = (atomicAdd(p.counters + tile, 1) == last - first);
-                }
+                if (et == 0) *s_flag = (atomicAdd(p.counters + tile, 1) == last_c - first_c);
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (*s_flag) {
                     __threadfence();
-                    if (f < p.N) {
 #pragma unroll
-                        for (int r = 0; r < BNX; ++r) {
-                            if (r < p.R) { float* sp = p.scratch + (long long)r * p.N + f; v[r] = __ldcg(sp); __stcg(sp, 0.f); } else v[r] = 0.f;
-                        }
+                    for (int r = 0; r < BNX; ++r) v[r] = 0.f;
+                    for (int c = first_c; c <= last_c; ++c) {
+                        const int slot = (tile == (c * p.chunk) / p.KB) ? 0 : 1;
+                        const float* src = p.scratch + (((long long)c * 2 + slot) * BNX) * BM + lane_grp * 32 + lane;
+#pragma unroll
+                        for (int r = 0; r < BNX; ++r)
+                            if (r < p.R) v[r] += __ldcg(src + r * BM);
                     }
                     if (et == 0) p.counters[tile] = 0;
-                    apply_epilogue<BNX>(p, f, lane, v);
+                    apply_epilogue<BNX>(p, f, lane, v, s_rs, part_row);
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");     // s_flag reusable
             }
@@ -264,19 +279,22 @@ int launch(const CUtensorMap& tw, const CUtensorMap& tx, const SkParams& p, int 
 
 extern "C" {
 
-int64_t br_skinny_scratch_bytes(int max_N) { return (int64_t)32 * max_N * sizeof(float) + (int64_t)(max_N / 128 + 2) * sizeof(int); }
+int64_t br_skinny_scratch_bytes(int max_N) {
+    // partial tiles [n_sms, 2, 32, 128] fp32 + one arrival counter per 128-feature tile
+    return (int64_t)br_num_sms() * 2 * 32 * BM * sizeof(float) + (int64_t)(max_N / BM + 2) * sizeof(int);
+}
 
 int br_skinny_gemm_ex(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
-                      const void* residual, int64_t ldr, void* scratch, const float* sumsq_in, float* sumsq_out, float* zero_buf, float eps,
+                      const void* residual, int64_t ldr, void* scratch, const float* sumsq_in, int sumsq_in_n, float* sumsq_out, float eps,
                       void* stream);
 
 int br_skinny_gemm(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
                    const void* residual, int64_t ldr, void* scratch, void* stream) {
-    return br_skinny_gemm_ex(X, ldx, W, ldw, out, ldo, R, N, K, mode, residual, ldr, scratch, nullptr, nullptr, nullptr, 0.f, stream);
+    return br_skinny_gemm_ex(X, ldx, W, ldw, out, ldo, R, N, K, mode, residual, ldr, scratch, nullptr, 0, nullptr, 0.f, stream);
 }
 
 int br_skinny_gemm_ex(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
-                      const void* residual, int64_t ldr, void* scratch, const float* sumsq_in, float* sumsq_out, float* zero_buf, float eps,
+                      const void* residual, int64_t ldr, void* scratch, const float* sumsq_in, int sumsq_in_n, float* sumsq_out, float eps,
                       void* stream) {
     BR_CHECK_ARG(R >= 1 && R <= 32, "skinny_gemm: R=%d must be in [1, 32]", R);
     BR_CHECK_ARG(N % 16 == 0 && K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "skinny_gemm: N %% 16, K %% 8, ld %% 8 (N=%d K=%d)", N, K);
@@ -284,8 +302,8 @@ int br_skinny_gemm_ex(const void* X, int64_t ldx, const void* W, int64_t ldw, vo
     BR_CHECK_ARG(scratch != nullptr, "skinny_gemm: scratch (br_skinny_scratch_bytes, zero-initialised once) is required");
     SkParams p;
     p.R = R; p.N = N; p.K = K; p.mode = mode; p.out = out; p.ldo = ldo; p.res = (const bf16*)residual; p.ldr = ldr;
-    p.scratch = (float*)scratch; p.counters = (int*)((float*)scratch + (int64_t)32 * N);
-    p.sumsq_in = sumsq_in; p.sumsq_out = sumsq_out; p.zero_buf = zero_buf; p.eps = eps;
+    p.scratch = (float*)scratch; p.counters = (int*)((float*)scratch + (int64_t)br_num_sms() * 2 * 32 * BM);
+    p.sumsq_in = sumsq_in; p.sumsq_in_n = sumsq_in_n; p.sumsq_out = sumsq_out; p.eps = eps;
     BR_CHECK_ARG(!(sumsq_out && mode >= 2), "skinny_gemm: sumsq_out only with bf16 outputs (mode 0/1)");
     p.tiles_n = (N + BM - 1) / BM; p.KB = (K + BK - 1) / BK; p.units = p.tiles_n * p.KB;
     int grid = p.units < br_num_sms() ? p.units : br_num_sms();

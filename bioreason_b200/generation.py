@@ -197,8 +197,10 @@ class RolloutEngine:
         attn_out = torch.empty(R, Hq * D, device=dev, dtype=torch.bfloat16)
         rope = ops.rope_table(max(plen) + C + 1, D, theta, dev)
         h = torch.empty(R, d, device=dev, dtype=torch.bfloat16)
-        ssq_a = torch.zeros(32, device=dev, dtype=torch.float32)            # sum x^2 of the residual stream entering attention
-        ssq_b = torch.zeros(32, device=dev, dtype=torch.float32)            # ... entering the MLP (ping-pong, see br_skinny_gemm_ex)
+        n_part = ((d + 127) // 128) * 4                                     # partial sum-of-squares rows a d-wide GEMM emits
+        ssq_a = torch.zeros(n_part, 32, device=dev, dtype=torch.float32)    # sum x^2 of the residual stream entering attention
+        ssq_b = torch.zeros(n_part, 32, device=dev, dtype=torch.float32)    # ... entering the MLP (see br_skinny_gemm_ex)
+        ssq_e = torch.zeros(1, 32, device=dev, dtype=torch.float32)         # ... of the embedding row (first layer)
 
         samp_ws = ops.sample_workspace(R, cfg.vocab_size, dev)
 
@@ -218,16 +220,16 @@ class RolloutEngine:
         def decode_step():
             # 5 launches per layer: qkv GEMM (folded ln1), fused attention, o_proj (+res, sum x^2), gate/up GEMM (folded ln2,
             # SwiGLU), down_proj (+res, sum x^2); RMSNorm never launches in the decode loop.
-            ops.embed_gather_sumsq(next_ids, Wd.embed, h, ssq_a)
+            ops.embed_gather_sumsq(next_ids, Wd.embed, h, ssq_e)
             x = h
             for li, Lw in enumerate(Wd.layers):
-                qkv = ops.skinny_gemm(x, Lw.w_qkv, scratch, sumsq_in=ssq_a, eps=eps)
+                qkv = ops.skinny_gemm(x, Lw.w_qkv, scratch, sumsq_in=ssq_e if li == 0 else ssq_a, sumsq_in_n=1 if li == 0 else n_part, eps=eps)
                 ops.decode_attn_fused(qkv, Lw.q_norm, Lw.k_norm, kc[li], vc[li], table, cur_len, G, Hq, Hkv, D, n_shared, splits_shared,
                                       splits_private, theta, eps, ws, attn_out, rope=rope)
-                x2 = ops.skinny_gemm(attn_out, Lw.w_o, scratch, mode=1, residual=x, sumsq_out=ssq_b, zero_buf=ssq_a)
-                act = ops.skinny_gemm(x2, Lw.w_gu, scratch, mode=2, sumsq_in=ssq_b, eps=eps)
-                x = ops.skinny_gemm(act, Lw.w_down, scratch, mode=1, residual=x2, sumsq_out=ssq_a, zero_buf=ssq_b)
-            lg = ops.skinny_gemm(x, Wd.lm_head, scratch, mode=3, sumsq_in=ssq_a, eps=eps)
+                x2 = ops.skinny_gemm(attn_out, Lw.w_o, scratch, mode=1, residual=x, sumsq_out=ssq_b)
+                act = ops.skinny_gemm(x2, Lw.w_gu, scratch, mode=2, sumsq_in=ssq_b, sumsq_in_n=n_part, eps=eps)
+                x = ops.skinny_gemm(act, Lw.w_down, scratch, mode=1, residual=x2, sumsq_out=ssq_a)
+            lg = ops.skinny_gemm(x, Wd.lm_head, scratch, mode=3, sumsq_in=ssq_a, sumsq_in_n=n_part, eps=eps)
             sample(lg)
             ops.decode_advance(step, cur_len)
 

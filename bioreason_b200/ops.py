@@ -237,7 +237,7 @@ def skinny_scratch(max_n: int, device) -> torch.Tensor:
     return torch.zeros(lib().br_skinny_scratch_bytes(max_n), device=device, dtype=torch.uint8)
 
 
-def skinny_gemm(x, w, scratch, *, mode=0, residual=None, out=None, sumsq_in=None, sumsq_out=None, zero_buf=None, eps=0.0):
+def skinny_gemm(x, w, scratch, *, mode=0, residual=None, out=None, sumsq_in=None, sumsq_in_n=1, sumsq_out=None, eps=0.0):
     """out[R, N] = x[R, K] @ w[N, K].T for R <= 32 decode rows (optionally with the folded-RMSNorm statistics)."""
     _need_cuda(x, w)
     R, K = x.shape
@@ -249,7 +249,8 @@ def skinny_gemm(x, w, scratch, *, mode=0, residual=None, out=None, sumsq_in=None
             out = torch.empty(R, N // 2 if mode == 2 else N, device=x.device, dtype=torch.bfloat16)
     check(lib().br_skinny_gemm_ex(ptr(x), _row_major_2d(x), ptr(w), _row_major_2d(w), ptr(out), _row_major_2d(out), R, N, K, mode,
                                   ptr(residual), _row_major_2d(residual) if residual is not None else 0, ptr(scratch),
-                                  ptr(sumsq_in, "float*"), ptr(sumsq_out, "float*"), ptr(zero_buf, "float*"), float(eps), _stream()),
+                                  ptr(sumsq_in, "float*"), int(sumsq_in_n) if sumsq_in is not None else 0, ptr(sumsq_out, "float*"),
+                                  float(eps), _stream()),
           "skinny_gemm")
     return out
 

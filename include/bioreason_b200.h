@@ -119,14 +119,15 @@ int br_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
  * ------------------------------------------------------------------------------------------- */
 int64_t br_skinny_scratch_bytes(int max_N);
 /* out[R, N] = X[R, K] . W[N, K]^T for R <= 32 (HBM-bound weight streaming). mode 0: bf16; 1: bf16(out) + residual;
- * 2: SwiGLU over (8 gate | 8 up) row blocks -> [R, N/2]; 3: fp32.  scratch: zero-initialised once, self-cleaning. */
+ * 2: SwiGLU over (8 gate | 8 up) row blocks -> [R, N/2]; 3: fp32.  scratch: zero-initialised once (arrival counters self-reset). */
 int br_skinny_gemm(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
                    const void* residual, int64_t ldr, void* scratch, void* stream);
 /* Same with a folded RMSNorm for the decode step (norm weight pre-multiplied into W's columns by br_scale_columns):
- * sumsq_in [R]: out rows are scaled by rsqrt(sumsq_in[r]/K + eps); sumsq_out [R] += sum_f out[r,f]^2 (bf16-rounded, modes 0/1);
- * zero_buf [32] is cleared (ping-pong statistic buffers).  Any of the three may be NULL. */
+ * sumsq_in [sumsq_in_n, 32]: partial sums of x^2 per row; out rows are scaled by rsqrt(sum_i sumsq_in[i, r] / K + eps);
+ * sumsq_out [ceil(N/128)*4, 32]: partial sums of the bf16-rounded outputs squared (modes 0/1), one partial row per 32
+ * features (so the consumer passes sumsq_in_n = ceil(N/128)*4).  No floating-point atomics: the rollout is reproducible. */
 int br_skinny_gemm_ex(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
-                      const void* residual, int64_t ldr, void* scratch, const float* sumsq_in, float* sumsq_out, float* zero_buf,
+                      const void* residual, int64_t ldr, void* scratch, const float* sumsq_in, int sumsq_in_n, float* sumsq_out,
                       float eps, void* stream);
 int br_embed_gather_sumsq(const int64_t* ids, const void* table, int64_t ldt, int64_t vocab, void* out, int64_t ldo, int M, int d,
                           float* sumsq, void* stream);

@@ -100,16 +100,17 @@ ws_l = [dict(qkv=torch.randn((Hq + 2 * Hkv) * D, d, device=dev).to(bf) * 0.02, o
              gu=torch.randn(2 * F, d, device=dev).to(bf) * 0.02, down=torch.randn(d, F, device=dev).to(bf) * 0.02) for _ in range(NL)]
 x0 = torch.randn(R, d, device=dev).to(bf)
 cur.fill_(T); step.zero_()          # decode_advance above moved them
-ssa = torch.ones(32, device=dev); ssb = torch.ones(32, device=dev)
+n_part = ((d + 127) // 128) * 4
+ssa = torch.ones(n_part, 32, device=dev); ssb = torch.ones(n_part, 32, device=dev)
 wsf = ops.decode_fused_workspace(R, Hq, Hkv, D, 10, dev)
 attn_out = torch.empty(R, Hq * D, device=dev, dtype=bf)
 def chain():
     x = x0
     for w in ws_l:
-        q = ops.skinny_gemm(x, w["qkv"], scratch, sumsq_in=ssa, eps=1e-6)
+        q = ops.skinny_gemm(x, w["qkv"], scratch, sumsq_in=ssa, sumsq_in_n=n_part, eps=1e-6)
         ops.decode_attn_fused(q, qn, kn, kc, vc, table, cur, G, Hq, Hkv, D, n_shared, 8, 2, 1e6, 1e-6, wsf, attn_out, rope=rope)
-        x2 = ops.skinny_gemm(attn_out, w["o"], scratch, mode=1, residual=x, sumsq_out=ssb, zero_buf=ssa)
-        a = ops.skinny_gemm(x2, w["gu"], scratch, mode=2, sumsq_in=ssb, eps=1e-6)
-        x = ops.skinny_gemm(a, w["down"], scratch, mode=1, residual=x2, sumsq_out=ssa, zero_buf=ssb)
+        x2 = ops.skinny_gemm(attn_out, w["o"], scratch, mode=1, residual=x, sumsq_out=ssb)
+        a = ops.skinny_gemm(x2, w["gu"], scratch, mode=2, sumsq_in=ssb, sumsq_in_n=n_part, eps=1e-6)
+        x = ops.skinny_gemm(a, w["down"], scratch, mode=1, residual=x2, sumsq_out=ssa)
 us = timed_graph(chain) / NL
 print(f"layer chain (5 launches): {us:8.2f} us per layer  -> {36 * us / 1e3:.3f} ms per token (36 layers)   PDL={'off' if os.environ.get('BR_NO_PDL') else 'on'}")
