@@ -15,6 +15,9 @@ using namespace attn;
 
 namespace {
 
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define STAMP(k) do { if (p.dbg && tid == 0) p.dbg[(long long)blockIdx.x * 8 + (k)] = gtime(); } while (0)
+
 __device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
 struct FusedParams {
@@ -28,6 +31,7 @@ struct FusedParams {
     float* part_o; float* part_lse; int* counters;      // [R,Hq,n_slots,D], [R,Hq,n_slots], [R*Hkv]
     bf16* out; long long ldo;
     float scale_log2, theta, eps;
+    long long* dbg;                      // optional [items, 8] globaltimer stamps (profiling aid)
     const float2* rope;                  // [n_pos, D/2] (cos, sin), bf16-rounded like HF's tables; may be null (computed inline)
     int rope_n_pos;
 };
@@ -88,8 +92,10 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
     __shared__ int s_last[64];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    STAMP(0);
     br::launch_dependents();
     br::grid_dep_wait();
+    STAMP(1);
     const int n_groups = p.R / p.G;
     const int n_shared_items = (p.n_shared_pages > 0 && p.SS > 0) ? n_groups * p.Hkv * p.SS : 0;
     int item = blockIdx.x;
@@ -165,6 +171,7 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
         }
     }
     __syncthreads();
+    STAMP(2);
 
     auto tile_src = [&](const bf16* cache, int pg) { return cache + (long long)table[pg] * page_stride + (long long)kvh * 64 * D; };
     if (pg_lo < pg_hi) {
@@ -179,6 +186,7 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
         ldsm_x4(qf[kk], tile_ptr<D>(sQ, warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, kk * 2 + (lane >> 4)));
     cp_async_wait<0>();
     __syncthreads();
+    STAMP(3);
 
     float o[D / 8][4];
 #pragma unroll
@@ -258,6 +266,7 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
         __syncthreads();
     }
 
+    STAMP(4);
     // ---- partials
     if (warp_live) {
         l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -282,10 +291,12 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
     }
     __threadfence();
     __syncthreads();
+    STAMP(5);
     // ---- arrival counters: one per (row, kv head); the last arriver merges the n_slots partials of its GQ heads
     if (tid < rows_per_unit && row_base + tid < p.R)
         s_last[tid] = (atomicAdd(p.counters + (row_base + tid) * p.Hkv + kvh, 1) == p.n_slots - 1);
     __syncthreads();
+    STAMP(6);
     // merge: weights w[h][s] = exp(lse - max) / sum are computed once into shared memory; every thread then issues its
     // n_slots partial loads back to back (independent, 16-byte) instead of a dependent chain of L2 round trips
     float* s_w = reinterpret_cast<float*>(smem);                      // [GQ][n_slots] (tile smem is free now)
@@ -321,11 +332,17 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
         }
         if (tid == 0) p.counters[row * p.Hkv + kvh] = 0;
     }
+    STAMP(7);
 }
 
 }  // namespace
 
+static long long* g_dbg = nullptr;
+
 extern "C" {
+
+/* profiling aid: [items, 8] int64 globaltimer stamps written by the next br_decode_attn_fused launches (NULL disables) */
+int br_decode_attn_fused_debug(long long* buf) { g_dbg = buf; return BR_OK; }
 
 int64_t br_decode_fused_workspace_bytes(int R, int n_q_heads, int n_kv_heads, int head_dim, int n_slots) {
     return (int64_t)R * n_q_heads * n_slots * (head_dim + 1) * sizeof(float) + (int64_t)R * n_kv_heads * sizeof(int);
@@ -361,6 +378,7 @@ int br_decode_attn_fused(const void* qkv_raw, int64_t ld, const void* q_norm_w, 
     p.counters = (int*)(p.part_lse + (int64_t)R * n_q_heads * p.n_slots);
     p.out = (bf16*)out; p.ldo = ldo; p.scale_log2 = scale * 1.4426950408889634f; p.theta = theta; p.eps = eps;
     p.rope = (const float2*)rope_table; p.rope_n_pos = rope_table ? rope_n_pos : 0;
+    p.dbg = g_dbg;
     constexpr int SMEM = 32 * D * 2 + 4 * 64 * D * 2;
     static bool done = false;
     if (!done) { BR_CHECK_CUDA(cudaFuncSetAttribute(decode_fused_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); done = true; }

@@ -242,12 +242,20 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     __threadfence();
 #pragma unroll
                     for (int r = 0; r < BNX; ++r) v[r] = 0.f;
-                    for (int c = first_c; c <= last_c; ++c) {
-                        const int slot = (tile == (c * p.chunk) / p.KB) ? 0 : 1;
-                        const float* src = p.scratch + (((long long)c * 2 + slot) * BNX) * BM + lane_grp * 32 + lane;
+                    for (int c0 = first_c; c0 <= last_c; c0 += 4) {             // 4 contributors' loads in flight at a time
+                        float t[4][BNX];
 #pragma unroll
-                        for (int r = 0; r < BNX; ++r)
-                            if (r < p.R) v[r] += __ldcg(src + r * BM);
+                        for (int j = 0; j < 4; ++j) {
+                            const int c = c0 + j;
+                            const int slot = (tile == (c * p.chunk) / p.KB) ? 0 : 1;
+                            const float* src = p.scratch + (((long long)c * 2 + slot) * BNX) * BM + lane_grp * 32 + lane;
+#pragma unroll
+                            for (int r = 0; r < BNX; ++r) t[j][r] = (c <= last_c && r < p.R) ? __ldcg(src + r * BM) : 0.f;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+#pragma unroll
+                            for (int r = 0; r < BNX; ++r) v[r] += t[j][r];                  // ascending CTA order: deterministic
                     }
                     if (et == 0) p.counters[tile] = 0;
                     apply_epilogue<BNX>(p, f, lane, v, s_rs, part_row);

@@ -32,7 +32,8 @@ def test_skinny_gemm(ops, R, N, K):
     r4 = ref.view(R, N // 16, 2, 8)
     g, u = r4[:, :, 0].reshape(R, N // 2).bfloat16().float(), r4[:, :, 1].reshape(R, N // 2).bfloat16().float()
     torch.testing.assert_close(o2.float(), torch.nn.functional.silu(g).bfloat16().float() * u, rtol=3e-2, atol=2e-2)
-    assert scratch.view(torch.int32).abs().sum().item() == 0
+    n_sms = torch.cuda.get_device_properties(0).multi_processor_count
+    assert scratch.view(torch.int32)[n_sms * 2 * 32 * 128:].abs().sum().item() == 0      # arrival counters self-reset
 
 
 def _dense_ref(q, kd, vd, kv_len, Hq, Hkv, D):
