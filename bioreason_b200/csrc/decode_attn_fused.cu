@@ -76,6 +76,46 @@ __device__ __forceinline__ void norm_rope_words(uint32_t wlo, uint32_t whi, cons
     }
 }
 
+// Quarter-warp version: 8 lanes own one 128-wide head vector (lane `sub` holds dims [8 sub, 8 sub + 8) of each half), so a warp
+// ropes 4 query vectors at once.  in/out: lo[8], hi[8] fp32.
+template <int D>
+__device__ __forceinline__ void norm_rope_q8(float (&lo)[8], float (&hi)[8], const bf16* __restrict__ w, int pos, int sub, float theta, float eps,
+                                             const float2* __restrict__ rope, int rope_n_pos) {
+    static_assert(D == 128, "head_dim 128");
+    float ss = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ss += lo[e] * lo[e] + hi[e] * hi[e];
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+    const float rstd = rsqrtf(ss / (float)D + eps);
+    const uint4 wl = __ldg(reinterpret_cast<const uint4*>(w + sub * 8)), wh = __ldg(reinterpret_cast<const uint4*>(w + 64 + sub * 8));
+    const uint32_t wls[4] = {wl.x, wl.y, wl.z, wl.w}, whs[4] = {wh.x, wh.y, wh.z, wh.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int j = sub * 8 + e;
+        const float2 wa = br::unpack_bf16(wls[e >> 1]), wb = br::unpack_bf16(whs[e >> 1]);
+        const float a = rbf(((e & 1) ? wa.y : wa.x) * rbf(lo[e] * rstd));
+        const float b = rbf(((e & 1) ? wb.y : wb.x) * rbf(hi[e] * rstd));
+        float sn, cs;
+        if (rope && pos < rope_n_pos) {
+            const float2 t = __ldg(rope + (long long)pos * (D / 2) + j);
+            cs = t.x; sn = t.y;
+        } else {
+            const float inv_freq = 1.0f / powf(theta, (float)(2 * j) / (float)D);
+            sincosf((float)pos * inv_freq, &sn, &cs);
+            sn = rbf(sn); cs = rbf(cs);
+        }
+        lo[e] = rbf(a * cs) + rbf(-b * sn);
+        hi[e] = rbf(b * cs) + rbf(a * sn);
+    }
+}
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    const float2 a = br::unpack_bf16(v.x), b = br::unpack_bf16(v.y), c = br::unpack_bf16(v.z), d = br::unpack_bf16(v.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    return make_uint4(br::pack_bf16(f[0], f[1]), br::pack_bf16(f[2], f[3]), br::pack_bf16(f[4], f[5]), br::pack_bf16(f[6], f[7]));
+}
+
 // L2 loads of the two 32-bit words a lane owns of a 128-wide bf16 head vector (PDL chain: never through L1)
 __device__ __forceinline__ void load_head_words(const bf16* src, int lane, uint32_t& wlo, uint32_t& whi) {
     wlo = __ldcg(reinterpret_cast<const unsigned int*>(src + lane * 2));
@@ -119,32 +159,36 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
 
     // ---- queries: norm + rope straight into the swizzled smem tile (slot s -> row s / GQ, head kvh*GQ + s % GQ)
     {
-        constexpr int NS = QROWS / 2;                        // slots per warp
-        uint32_t wlo[NS], whi[NS]; int posv[NS];
+        // 8 lanes per query vector, 4 vectors per warp per pass, 4 passes: all 16-byte L2 loads are issued before any is used
+        const int q4 = lane >> 3, sub = lane & 7;
+        uint4 rl[4], rh[4]; int posv[4];
 #pragma unroll
-        for (int i = 0; i < NS; ++i) {                        // all loads in flight before any of them is consumed
-            const int s = warp + 2 * i;
+        for (int i = 0; i < 4; ++i) {
+            const int s = warp * 16 + i * 4 + q4;
             const int rr = s / p.GQ, hh = kvh * p.GQ + s % p.GQ;
             const bool ok = rr < rows_per_unit && (row_base + rr) < p.R;
-            wlo[i] = whi[i] = 0u; posv[i] = -1;
+            rl[i] = rh[i] = make_uint4(0, 0, 0, 0); posv[i] = -1;
             if (ok) {
                 const int row = row_base + rr;
-                load_head_words(p.qkv + (long long)row * p.ld + (long long)hh * D, lane, wlo[i], whi[i]);
+                const bf16* src = p.qkv + (long long)row * p.ld + (long long)hh * D;
+                rl[i] = __ldcg(reinterpret_cast<const uint4*>(src + sub * 8));
+                rh[i] = __ldcg(reinterpret_cast<const uint4*>(src + 64 + sub * 8));
                 posv[i] = __ldcg(p.cur_len + row);
             }
         }
 #pragma unroll
-        for (int i = 0; i < NS; ++i) {
-            const int s = warp + 2 * i;
-            float olo[E], ohi[E];
-            if (posv[i] >= 0) norm_rope_words<D>(wlo[i], whi[i], p.qw, posv[i], p.theta, p.eps, lane, olo, ohi, p.rope, p.rope_n_pos);
-            else {
+        for (int i = 0; i < 4; ++i) {
+            const int s = warp * 16 + i * 4 + q4;
+            float lo[8], hi[8];
+            unpack8(rl[i], lo); unpack8(rh[i], hi);
+            // all 8 lanes of a vector take the same branch; shuffles inside use the full mask, so keep the warp converged
+            norm_rope_q8<D>(lo, hi, p.qw, posv[i] < 0 ? 0 : posv[i], sub, p.theta, p.eps, p.rope, p.rope_n_pos);
+            if (posv[i] < 0) {
 #pragma unroll
-                for (int e = 0; e < E; ++e) olo[e] = ohi[e] = 0.f;
+                for (int e = 0; e < 8; ++e) lo[e] = hi[e] = 0.f;
             }
-            const int j0 = lane * E;
-            *reinterpret_cast<uint32_t*>(tile_ptr<D>(sQ, s, j0 >> 3) + (j0 & 7) * 2) = br::pack_bf16(olo[0], olo[1]);
-            *reinterpret_cast<uint32_t*>(tile_ptr<D>(sQ, s, (D / 2 + j0) >> 3) + (j0 & 7) * 2) = br::pack_bf16(ohi[0], ohi[1]);
+            *reinterpret_cast<uint4*>(tile_ptr<D>(sQ, s, sub)) = pack8(lo);
+            *reinterpret_cast<uint4*>(tile_ptr<D>(sQ, s, 8 + sub)) = pack8(hi);
         }
     }
     // ---- append the new token's K / V (private item that owns the newest page)
@@ -297,40 +341,44 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
         s_last[tid] = (atomicAdd(p.counters + (row_base + tid) * p.Hkv + kvh, 1) == p.n_slots - 1);
     __syncthreads();
     STAMP(6);
-    // merge: weights w[h][s] = exp(lse - max) / sum are computed once into shared memory; every thread then issues its
-    // n_slots partial loads back to back (independent, 16-byte) instead of a dependent chain of L2 round trips
-    float* s_w = reinterpret_cast<float*>(smem);                      // [GQ][n_slots] (tile smem is free now)
-    for (int rr = 0; rr < rows_per_unit; ++rr) {
-        if (row_base + rr >= p.R || !s_last[rr]) continue;            // block-uniform
+    // merge (all rows this CTA is the last arriver for, in one pass): thread (row, head) turns the n_slots LSEs into weights in
+    // shared memory; then every thread issues its independent 16-byte partial loads back to back (L2, fixed slot order).
+    float* s_w = reinterpret_cast<float*>(smem);                      // [rows_per_unit * GQ][n_slots] (tile smem is free now)
+    bool any = false;
+    for (int rr = 0; rr < rows_per_unit; ++rr) any |= (row_base + rr < p.R) && s_last[rr];
+    if (any) {
         __threadfence();
-        const int row = row_base + rr;
-        __syncthreads();
-        if (tid < p.GQ) {
-            const float* lse = p.part_lse + ((long long)row * p.Hq + kvh * p.GQ + tid) * p.n_slots;
-            float l[32];
+        for (int pair = tid; pair < rows_per_unit * p.GQ; pair += NT) {
+            const int rr = pair / p.GQ, hl = pair % p.GQ;
+            if (row_base + rr >= p.R || !s_last[rr]) continue;
+            const float* lse = p.part_lse + ((long long)(row_base + rr) * p.Hq + kvh * p.GQ + hl) * p.n_slots;
             float mx = -INFINITY;
-            for (int s = 0; s < p.n_slots; ++s) { l[s] = __ldcg(lse + s); mx = fmaxf(mx, l[s]); }
+            for (int s2 = 0; s2 < p.n_slots; ++s2) mx = fmaxf(mx, __ldcg(lse + s2));
             float den = 0.f;
-            for (int s = 0; s < p.n_slots; ++s) { l[s] = (l[s] == -INFINITY) ? 0.f : __expf(l[s] - mx); den += l[s]; }
+            for (int s2 = 0; s2 < p.n_slots; ++s2) { const float l = __ldcg(lse + s2); den += (l == -INFINITY) ? 0.f : __expf(l - mx); }
             const float inv = den > 0.f ? 1.f / den : 0.f;
-            for (int s = 0; s < p.n_slots; ++s) s_w[tid * p.n_slots + s] = l[s] * inv;
+            for (int s2 = 0; s2 < p.n_slots; ++s2) { const float l = __ldcg(lse + s2); s_w[pair * p.n_slots + s2] = (l == -INFINITY) ? 0.f : __expf(l - mx) * inv; }
         }
         __syncthreads();
-        for (int idx = tid; idx < p.GQ * (D / 4); idx += NT) {
-            const int hl = idx / (D / 4), d4 = (idx % (D / 4)) * 4;
-            const int hq = kvh * p.GQ + hl;
+        const int per_row = p.GQ * (D / 4);
+        for (int idx = tid; idx < rows_per_unit * per_row; idx += NT) {
+            const int rr = idx / per_row, rem = idx % per_row;
+            if (row_base + rr >= p.R || !s_last[rr]) continue;
+            const int hl = rem / (D / 4), d4 = (rem % (D / 4)) * 4;
+            const int row = row_base + rr, hq = kvh * p.GQ + hl;
             const float* po = p.part_o + ((long long)row * p.Hq + hq) * p.n_slots * D + d4;
+            const float* wv = s_w + (rr * p.GQ + hl) * p.n_slots;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-            for (int s = 0; s < p.n_slots; ++s) {
-                const float w = s_w[hl * p.n_slots + s];
-                const float4 v = __ldcg(reinterpret_cast<const float4*>(po + (long long)s * D));
+            for (int s2 = 0; s2 < p.n_slots; ++s2) {
+                const float w = wv[s2];
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(po + (long long)s2 * D));
                 acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
             }
             *reinterpret_cast<uint2*>(p.out + (long long)row * p.ldo + (long long)hq * D + d4) =
                 make_uint2(br::pack_bf16(acc.x, acc.y), br::pack_bf16(acc.z, acc.w));
         }
-        if (tid == 0) p.counters[row * p.Hkv + kvh] = 0;
+        if (tid < rows_per_unit && row_base + tid < p.R && s_last[tid]) p.counters[(row_base + tid) * p.Hkv + kvh] = 0;
     }
     STAMP(7);
 }
