@@ -336,11 +336,27 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
     __threadfence();
     __syncthreads();
     STAMP(5);
-    // ---- arrival counters: one per (row, kv head); the last arriver merges the n_slots partials of its GQ heads
-    if (tid < rows_per_unit && row_base + tid < p.R)
-        s_last[tid] = (atomicAdd(p.counters + (row_base + tid) * p.Hkv + kvh, 1) == p.n_slots - 1);
+    // ---- arrival counters: one per (row, kv head).  The private split-0 item of a (row, kv head) pair is its merger: it waits for
+    //      the other n_slots - 1 partials and merges them, so the 64 merges of a step run on 64 different CTAs in parallel
+    //      (a "last arriver merges" scheme serialises all 8 rows of a group on one late shared item).  All items of a launch are
+    //      co-resident (checked on the host), so the bounded spin cannot deadlock.
+    const bool merger = !shared_pass && split == 0;
+    if (!merger) {
+        if (tid < rows_per_unit && row_base + tid < p.R) atomicAdd(p.counters + (row_base + tid) * p.Hkv + kvh, 1);
+        STAMP(6); STAMP(7);
+        return;
+    }
+    if (tid == 0) {
+        const int* c = p.counters + row_base * p.Hkv + kvh;
+        int seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(c) : "memory");
+            if (seen < p.n_slots - 1) __nanosleep(40);
+        } while (seen < p.n_slots - 1);
+    }
     __syncthreads();
-    STAMP(6);
+    s_last[0] = 1;                                                 // rows_per_unit == 1 here
+    __syncthreads();
     // merge (all rows this CTA is the last arriver for, in one pass): thread (row, head) turns the n_slots LSEs into weights in
     // shared memory; then every thread issues its independent 16-byte partial loads back to back (L2, fixed slot order).
     float* s_w = reinterpret_cast<float*>(smem);                      // [rows_per_unit * GQ][n_slots] (tile smem is free now)
@@ -378,7 +394,7 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
             *reinterpret_cast<uint2*>(p.out + (long long)row * p.ldo + (long long)hq * D + d4) =
                 make_uint2(br::pack_bf16(acc.x, acc.y), br::pack_bf16(acc.z, acc.w));
         }
-        if (tid < rows_per_unit && row_base + tid < p.R && s_last[tid]) p.counters[(row_base + tid) * p.Hkv + kvh] = 0;
+        if (tid == 0) p.counters[row_base * p.Hkv + kvh] = 0;
     }
     STAMP(7);
 }
@@ -431,6 +447,7 @@ int br_decode_attn_fused(const void* qkv_raw, int64_t ld, const void* q_norm_w, 
     static bool done = false;
     if (!done) { BR_CHECK_CUDA(cudaFuncSetAttribute(decode_fused_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); done = true; }
     const int items = (use_shared ? (R / G) * n_kv_heads * p.SS : 0) + R * n_kv_heads * p.SP;
+    BR_CHECK_ARG(items <= 3 * br_num_sms(), "decode_attn_fused: %d work items exceed the co-resident capacity (3 per SM) the in-kernel merge relies on", items);
     BR_CHECK_CUDA(br_launch_pdl(decode_fused_kernel<D>, dim3(items), dim3(64), (size_t)SMEM, (cudaStream_t)stream, p));
     return BR_OK;
 }
