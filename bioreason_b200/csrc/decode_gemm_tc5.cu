@@ -283,13 +283,243 @@ int launch(const CUtensorMap& tw, const CUtensorMap& tx, const SkParams& p, int 
     return BR_OK;
 }
 
+
+// ================================================================================================================
+// Multi-phase persistent variant: up to 4 dependent GEMMs (o_proj -> gate/up -> down_proj -> next layer's qkv, or
+// ... -> lm_head) in ONE launch.  Phases are separated by a grid-wide barrier instead of a kernel boundary; the weight
+// producer is not gated by the barrier, so while the CTAs synchronise (and while the last tiles of a phase are reduced)
+// the ring already fills with the next phase's weights -- the HBM stream does not stop at phase boundaries.  A second
+// producer thread loads the activation tiles and is the only one that waits for "phase inputs ready".
+// ================================================================================================================
+constexpr int CHAIN_MAX = 4;
+constexpr int CHAIN_THREADS = 224;           // warp 0: W producer, 1: MMA, 2-5: epilogue, 6: X producer
+
+struct ChainPhase { CUtensorMap tmW; CUtensorMap tmX; SkParams p; };
+struct ChainParams { ChainPhase ph[CHAIN_MAX]; int n_phases; int* gbar; };
+
+template <int BNX>
+__global__ void __launch_bounds__(CHAIN_THREADS, 1) skinny_chain_kernel(const __grid_constant__ ChainParams cp) {
+    using L = SL<BNX>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::TILE_BYTES);
+    uint64_t* empty_bar = full_bar + L::NSTAGE;
+    uint64_t* tfull_bar = empty_bar + L::NSTAGE;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
+    volatile int* s_ready = reinterpret_cast<volatile int*>(s_flag + 1);      // number of grid barriers this CTA has passed
+    float* s_rs = reinterpret_cast<float*>(s_flag + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nph = cp.n_phases;
+
+    br::launch_dependents();
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < nph; ++i) { br::tma_prefetch_desc(&cp.ph[i].tmW); br::tma_prefetch_desc(&cp.ph[i].tmX); }
+        for (int s = 0; s < L::NSTAGE; ++s) { br::mbar_init(&full_bar[s], 1); br::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { br::mbar_init(&tfull_bar[s], 1); br::mbar_init(&tempty_bar[s], 4); }
+        br::mbar_fence_init();
+        *s_ready = 0;
+    }
+    if (warp == 1) {
+        br::tmem_alloc(tmem_slot, 2 * BNX < 32 ? 32 : 2 * BNX);
+        br::tmem_relinquish();
+    }
+    br::tc_fence_before();
+    __syncthreads();
+    br::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- weight producer: never waits for other kernels or phases (weights are constant) ----------------
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int pi = 0; pi < nph; ++pi) {
+                const SkParams& p = cp.ph[pi].p;
+                const int u_lo = blockIdx.x * p.chunk, u_hi = min(p.units, u_lo + p.chunk);
+                for (int u = u_lo; u < u_hi; ++u) {
+                    const int tile = u / p.KB, kb = u - tile * p.KB;
+                    br::mbar_wait(&empty_bar[s], ph ^ 1);
+                    br::mbar_expect_tx(&full_bar[s], L::STAGE);
+                    br::tma_load_2d(smem + s * L::STAGE, &cp.ph[pi].tmW, &full_bar[s], kb * BK, tile * BM);
+                    if (++s == L::NSTAGE) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 6) {
+        // ---------------- activation producer: gated by "inputs of phase pi are complete" ----------------
+        if (lane == 0) {
+            br::grid_dep_wait();
+            int s = 0; uint32_t ph = 0;
+            for (int pi = 0; pi < nph; ++pi) {
+                const SkParams& p = cp.ph[pi].p;
+                const int u_lo = blockIdx.x * p.chunk, u_hi = min(p.units, u_lo + p.chunk);
+                if (u_lo < u_hi) while (*s_ready < pi) __nanosleep(32);
+                for (int u = u_lo; u < u_hi; ++u) {
+                    const int tile = u / p.KB, kb = u - tile * p.KB;
+                    br::mbar_wait(&empty_bar[s], ph ^ 1);
+                    br::tma_load_2d(smem + s * L::STAGE + L::A_BYTES, &cp.ph[pi].tmX, &full_bar[s], kb * BK, 0);
+                    if (++s == L::NSTAGE) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = br::make_idesc_bf16(BM, BNX);
+            int s = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0;
+            for (int pi = 0; pi < nph; ++pi) {
+                const SkParams& p = cp.ph[pi].p;
+                const int u_lo = blockIdx.x * p.chunk, u_hi = min(p.units, u_lo + p.chunk);
+                int u = u_lo;
+                while (u < u_hi) {
+                    const int tile = u / p.KB;
+                    const int seg_end = min(u_hi, (tile + 1) * p.KB);
+                    br::mbar_wait(&tempty_bar[as], aph ^ 1);
+                    br::tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + as * BNX;
+                    for (int i = 0; u < seg_end; ++u, ++i) {
+                        br::mbar_wait(&full_bar[s], ph);
+                        br::tc_fence_after();
+                        const uint32_t sa = br::smem_u32(smem + s * L::STAGE);
+                        const uint64_t adesc = br::make_sw128_kmajor_desc(sa);
+                        const uint64_t bdesc = br::make_sw128_kmajor_desc(sa + L::A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) br::tc_mma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
+                        br::tc_commit(&empty_bar[s]);
+                        if (++s == L::NSTAGE) { s = 0; ph ^= 1; }
+                    }
+                    br::tc_commit(&tfull_bar[as]);
+                    if (++as == 2) { as = 0; aph ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ---------------- epilogue warps 2..5 ----------------
+        const int lane_grp = warp & 3;
+        const int et = threadIdx.x - 64;
+        br::grid_dep_wait();
+        int as = 0; uint32_t aph = 0;
+        for (int pi = 0; pi < nph; ++pi) {
+            const SkParams& p = cp.ph[pi].p;
+            const int u_lo = blockIdx.x * p.chunk, u_hi = min(p.units, u_lo + p.chunk);
+            if (et < 32) {                                    // per-row rstd of the folded RMSNorm (inputs complete: barrier pi-1 passed)
+                float rsv = 1.f;
+                if (p.sumsq_in && et < p.R) {
+                    float acc = 0.f;
+                    for (int i = 0; i < p.sumsq_in_n; ++i) acc += __ldcg(p.sumsq_in + (long long)i * 32 + et);
+                    rsv = rsqrtf(acc / (float)p.K + p.eps);
+                }
+                s_rs[et] = rsv;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            int u = u_lo;
+            while (u < u_hi) {
+                const int tile = u / p.KB;
+                const int seg_end = min(u_hi, (tile + 1) * p.KB);
+                const bool whole = (u == tile * p.KB) && (seg_end == (tile + 1) * p.KB);
+                br::mbar_wait(&tfull_bar[as], aph);
+                br::tc_fence_after();
+                const uint32_t taddr = tmem_base + as * BNX + ((uint32_t)(lane_grp * 32) << 16);
+                float v[BNX];
+#pragma unroll
+                for (int c = 0; c < BNX; c += 16) {
+                    uint32_t r[16];
+                    __syncwarp();
+                    tmem_ld_32x16(taddr + c, r);
+                    br::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[c + i] = __uint_as_float(r[i]);
+                }
+                br::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) br::mbar_arrive(&tempty_bar[as]);
+                if (++as == 2) { as = 0; aph ^= 1; }
+                const int f = tile * BM + lane_grp * 32 + lane;
+                const int part_row = tile * 4 + lane_grp;
+                if (whole) {
+                    apply_epilogue<BNX>(p, f, lane, v, s_rs, part_row);
+                } else {
+                    const int first_c = (tile * p.KB) / p.chunk, last_c = ((tile + 1) * p.KB - 1) / p.chunk;
+                    const int my_slot = (tile == u_lo / p.KB) ? 0 : 1;
+                    float* mine = p.scratch + (((long long)blockIdx.x * 2 + my_slot) * BNX) * BM + lane_grp * 32 + lane;
+#pragma unroll
+                    for (int r = 0; r < BNX; ++r)
+                        if (r < p.R) __stcg(mine + r * BM, v[r]);
+                    __threadfence();
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (et == 0) *s_flag = (atomicAdd(p.counters + tile, 1) == last_c - first_c);
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (*s_flag) {
+                        __threadfence();
+#pragma unroll
+                        for (int r = 0; r < BNX; ++r) v[r] = 0.f;
+                        for (int c0 = first_c; c0 <= last_c; c0 += 4) {
+                            float t[4][BNX];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int c = c0 + j;
+                                const int slot = (tile == (c * p.chunk) / p.KB) ? 0 : 1;
+                                const float* src = p.scratch + (((long long)c * 2 + slot) * BNX) * BM + lane_grp * 32 + lane;
+#pragma unroll
+                                for (int r = 0; r < BNX; ++r) t[j][r] = (c <= last_c && r < p.R) ? __ldcg(src + r * BM) : 0.f;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                                for (int r = 0; r < BNX; ++r) v[r] += t[j][r];
+                        }
+                        if (et == 0) p.counters[tile] = 0;
+                        apply_epilogue<BNX>(p, f, lane, v, s_rs, part_row);
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                u = seg_end;
+            }
+            if (pi + 1 < nph) {
+                // grid barrier: every CTA's outputs of phase pi are globally visible before anyone loads them as phase pi+1 inputs
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) {
+                    atomicAdd(cp.gbar, 1);
+                    const int target = (pi + 1) * (int)gridDim.x;
+                    int seen;
+                    do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(cp.gbar) : "memory"); } while (seen < target);
+                    *s_ready = pi + 1;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+        }
+        // the last CTA to finish re-zeros the barrier words for the next launch (everyone else has left the barrier code)
+        if (et == 0 && nph > 1) {
+            if (atomicAdd(cp.gbar + 1, 1) == (int)gridDim.x - 1) { cp.gbar[0] = 0; cp.gbar[1] = 0; __threadfence(); }
+        }
+    }
+    br::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        br::tc_fence_after();
+        br::tmem_dealloc(tmem_base, 2 * BNX < 32 ? 32 : 2 * BNX);
+    }
+}
+
+template <int BNX>
+int launch_chain(const ChainParams& cp, int grid, cudaStream_t st) {
+    using L = SL<BNX>;
+    auto kern = skinny_chain_kernel<BNX>;
+    static bool done = false;
+    if (!done) { BR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL)); done = true; }
+    BR_CHECK_CUDA(br_launch_pdl(kern, dim3(grid), dim3(CHAIN_THREADS), (size_t)L::TOTAL, st, cp));
+    return BR_OK;
+}
+
 }  // namespace
 
 extern "C" {
 
 int64_t br_skinny_scratch_bytes(int max_N) {
-    // partial tiles [n_sms, 2, 32, 128] fp32 + one arrival counter per 128-feature tile
-    return (int64_t)br_num_sms() * 2 * 32 * BM * sizeof(float) + (int64_t)(max_N / BM + 2) * sizeof(int);
+    // partial tiles [n_sms, 2, 32, 128] fp32 | grid-barrier word (16 ints) | one arrival counter per 128-feature tile
+    return (int64_t)br_num_sms() * 2 * 32 * BM * sizeof(float) + 16 * sizeof(int) + (int64_t)(max_N / BM + 2) * sizeof(int);
 }
 
 int br_skinny_gemm_ex(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
@@ -310,7 +540,7 @@ int br_skinny_gemm_ex(const void* X, int64_t ldx, const void* W, int64_t ldw, vo
     BR_CHECK_ARG(scratch != nullptr, "skinny_gemm: scratch (br_skinny_scratch_bytes, zero-initialised once) is required");
     SkParams p;
     p.R = R; p.N = N; p.K = K; p.mode = mode; p.out = out; p.ldo = ldo; p.res = (const bf16*)residual; p.ldr = ldr;
-    p.scratch = (float*)scratch; p.counters = (int*)((float*)scratch + (int64_t)br_num_sms() * 2 * 32 * BM);
+    p.scratch = (float*)scratch; p.counters = (int*)((float*)scratch + (int64_t)br_num_sms() * 2 * 32 * BM) + 16;
     p.sumsq_in = sumsq_in; p.sumsq_in_n = sumsq_in_n; p.sumsq_out = sumsq_out; p.eps = eps;
     BR_CHECK_ARG(!(sumsq_out && mode >= 2), "skinny_gemm: sumsq_out only with bf16 outputs (mode 0/1)");
     p.tiles_n = (N + BM - 1) / BM; p.KB = (K + BK - 1) / BK; p.units = p.tiles_n * p.KB;
@@ -324,6 +554,34 @@ int br_skinny_gemm_ex(const void* X, int64_t ldx, const void* W, int64_t ldw, vo
     if ((rc = br_make_tmap_2d_bf16(&tx, X, R, K, ldx, BNX))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     return BNX == 16 ? launch<16>(tw, tx, p, grid, st) : launch<32>(tw, tx, p, grid, st);
+}
+
+
+int br_skinny_chain(const br_skinny_phase* phases, int n_phases, int R, float eps, void* scratch, void* stream) {
+    BR_CHECK_ARG(n_phases >= 1 && n_phases <= CHAIN_MAX && R >= 1 && R <= 32 && scratch, "skinny_chain: 1..%d phases, R in [1, 32]", CHAIN_MAX);
+    ChainParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.n_phases = n_phases;
+    const int BNX = R <= 16 ? 16 : 32;
+    const int grid = br_num_sms();                         // every phase uses the full grid: the barrier counts gridDim.x arrivals
+    float* part = (float*)scratch;
+    cp.gbar = (int*)(part + (int64_t)br_num_sms() * 2 * 32 * BM);
+    for (int i = 0; i < n_phases; ++i) {
+        const br_skinny_phase& h = phases[i];
+        BR_CHECK_ARG(h.N % 16 == 0 && h.K % 8 == 0 && h.ldx % 8 == 0 && h.ldw % 8 == 0, "skinny_chain[%d]: N %% 16, K %% 8, ld %% 8", i);
+        BR_CHECK_ARG(h.mode >= 0 && h.mode <= 3 && !(h.mode == 1 && !h.residual) && !(h.sumsq_out && h.mode >= 2), "skinny_chain[%d]: bad mode", i);
+        SkParams& p = cp.ph[i].p;
+        p.R = R; p.N = h.N; p.K = h.K; p.mode = h.mode; p.out = h.out; p.ldo = h.ldo; p.res = (const bf16*)h.residual; p.ldr = h.ldr;
+        p.scratch = part; p.counters = cp.gbar + 16;
+        p.sumsq_in = h.sumsq_in; p.sumsq_in_n = h.sumsq_in_n; p.sumsq_out = h.sumsq_out; p.eps = eps;
+        p.tiles_n = (h.N + BM - 1) / BM; p.KB = (h.K + BK - 1) / BK; p.units = p.tiles_n * p.KB;
+        p.chunk = (p.units + grid - 1) / grid;
+        int rc;
+        if ((rc = br_make_tmap_2d_bf16(&cp.ph[i].tmW, h.W, h.N, h.K, h.ldw, BM))) return rc;
+        if ((rc = br_make_tmap_2d_bf16(&cp.ph[i].tmX, h.X, R, h.K, h.ldx, BNX))) return rc;
+    }
+    cudaStream_t st = (cudaStream_t)stream;      // barrier words gbar[0..1] are zero between launches (self-resetting)
+    return BNX == 16 ? launch_chain<16>(cp, grid, st) : launch_chain<32>(cp, grid, st);
 }
 
 }  // extern "C"

@@ -217,20 +217,30 @@ class RolloutEngine:
         sample(logits)
         step += 1                                                         # cur_len stays: the first generated token sits at index plen
 
+        F = cfg.intermediate_size
+        b_qkv = torch.empty(R, (Hq + 2 * Hkv) * D, device=dev, dtype=torch.bfloat16)
+        b_x2 = torch.empty(R, d, device=dev, dtype=torch.bfloat16)
+        b_act = torch.empty(R, F, device=dev, dtype=torch.bfloat16)
+        b_logits = torch.empty(R, cfg.vocab_size, device=dev, dtype=torch.float32)
+
         def decode_step():
-            # 5 launches per layer: qkv GEMM (folded ln1), fused attention, o_proj (+res, sum x^2), gate/up GEMM (folded ln2,
-            # SwiGLU), down_proj (+res, sum x^2); RMSNorm never launches in the decode loop.
+            # 2 launches per layer: fused attention, then ONE persistent kernel running o_proj (+res) -> gate/up (folded ln2, SwiGLU)
+            # -> down_proj (+res) -> the NEXT layer's qkv projection (folded ln1) / the lm_head, with grid barriers inside.
+            # RMSNorm never launches: its statistics ride along in the GEMM epilogues (sum x^2 partials).
             ops.embed_gather_sumsq(next_ids, Wd.embed, h, ssq_e)
-            x = h
+            L0 = Wd.layers[0]
+            ops.skinny_gemm(h, L0.w_qkv, scratch, out=b_qkv, sumsq_in=ssq_e, sumsq_in_n=1, eps=eps)
+            nl_ = len(Wd.layers)
             for li, Lw in enumerate(Wd.layers):
-                qkv = ops.skinny_gemm(x, Lw.w_qkv, scratch, sumsq_in=ssq_e if li == 0 else ssq_a, sumsq_in_n=1 if li == 0 else n_part, eps=eps)
-                ops.decode_attn_fused(qkv, Lw.q_norm, Lw.k_norm, kc[li], vc[li], table, cur_len, G, Hq, Hkv, D, n_shared, splits_shared,
+                ops.decode_attn_fused(b_qkv, Lw.q_norm, Lw.k_norm, kc[li], vc[li], table, cur_len, G, Hq, Hkv, D, n_shared, splits_shared,
                                       splits_private, theta, eps, ws, attn_out, rope=rope)
-                x2 = ops.skinny_gemm(attn_out, Lw.w_o, scratch, mode=1, residual=x, sumsq_out=ssq_b)
-                act = ops.skinny_gemm(x2, Lw.w_gu, scratch, mode=2, sumsq_in=ssq_b, sumsq_in_n=n_part, eps=eps)
-                x = ops.skinny_gemm(act, Lw.w_down, scratch, mode=1, residual=x2, sumsq_out=ssq_a)
-            lg = ops.skinny_gemm(x, Wd.lm_head, scratch, mode=3, sumsq_in=ssq_a, sumsq_in_n=n_part, eps=eps)
-            sample(lg)
+                nxt = (dict(x=h, w=Wd.layers[li + 1].w_qkv, out=b_qkv, mode=0, sumsq_in=ssq_a, sumsq_in_n=n_part) if li + 1 < nl_ else
+                       dict(x=h, w=Wd.lm_head, out=b_logits, mode=3, sumsq_in=ssq_a, sumsq_in_n=n_part))
+                ops.skinny_chain([dict(x=attn_out, w=Lw.w_o, out=b_x2, mode=1, residual=h, sumsq_out=ssq_b),
+                                  dict(x=b_x2, w=Lw.w_gu, out=b_act, mode=2, sumsq_in=ssq_b, sumsq_in_n=n_part),
+                                  dict(x=b_act, w=Lw.w_down, out=h, mode=1, residual=b_x2, sumsq_out=ssq_a),
+                                  nxt], R, scratch, eps=eps)
+            sample(b_logits)
             ops.decode_advance(step, cur_len)
 
         n_steps = C - 1

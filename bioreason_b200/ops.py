@@ -255,6 +255,26 @@ def skinny_gemm(x, w, scratch, *, mode=0, residual=None, out=None, sumsq_in=None
     return out
 
 
+def skinny_chain(phases, R, scratch, eps=0.0):
+    """phases: list of dicts(x, w, out, mode=0, residual=None, sumsq_in=None, sumsq_in_n=1, sumsq_out=None) -- up to 4
+    dependent decode GEMMs in one persistent launch (grid barrier between phases, weights prefetched across it)."""
+    n = len(phases)
+    arr = ffi.new("br_skinny_phase[]", n)
+    keep = []
+    for i, ph in enumerate(phases):
+        x, w, out = ph["x"], ph["w"], ph["out"]
+        a = arr[i]
+        a.X = ptr(x); a.ldx = _row_major_2d(x); a.W = ptr(w); a.ldw = _row_major_2d(w); a.out = ptr(out); a.ldo = _row_major_2d(out)
+        a.N = w.shape[0]; a.K = w.shape[1]; a.mode = ph.get("mode", 0)
+        res = ph.get("residual")
+        a.residual = ptr(res); a.ldr = _row_major_2d(res) if res is not None else 0
+        si = ph.get("sumsq_in")
+        a.sumsq_in = ptr(si, "float*"); a.sumsq_in_n = int(ph.get("sumsq_in_n", 1)) if si is not None else 0
+        a.sumsq_out = ptr(ph.get("sumsq_out"), "float*")
+        keep += [x, w, out, res, si]
+    check(lib().br_skinny_chain(arr, n, R, float(eps), ptr(scratch), _stream()), "skinny_chain")
+
+
 def embed_gather_sumsq(ids, table, out, sumsq):
     ids = ids.reshape(-1)
     assert ids.dtype == torch.int64

@@ -129,6 +129,19 @@ int br_skinny_gemm(const void* X, int64_t ldx, const void* W, int64_t ldw, void*
 int br_skinny_gemm_ex(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
                       const void* residual, int64_t ldr, void* scratch, const float* sumsq_in, int sumsq_in_n, float* sumsq_out,
                       float eps, void* stream);
+/* Up to 4 dependent decode GEMMs in ONE persistent launch (e.g. o_proj -> gate/up -> down_proj -> next layer's qkv):
+ * phases are separated by a grid-wide barrier inside the kernel and the weight producer prefetches across it, so the
+ * HBM stream does not stall at layer boundaries.  Same per-phase semantics as br_skinny_gemm_ex. */
+typedef struct br_skinny_phase {
+    const void* X; int64_t ldx;         /* [R, K] bf16 input (for phases > 0: the output of an earlier phase) */
+    const void* W; int64_t ldw;         /* [N, K] bf16 weight */
+    void* out; int64_t ldo;
+    int32_t N, K, mode;
+    const void* residual; int64_t ldr;
+    const float* sumsq_in; int32_t sumsq_in_n;
+    float* sumsq_out;
+} br_skinny_phase;
+int br_skinny_chain(const br_skinny_phase* phases, int n_phases, int R, float eps, void* scratch, void* stream);
 int br_embed_gather_sumsq(const int64_t* ids, const void* table, int64_t ldt, int64_t vocab, void* out, int64_t ldo, int M, int d,
                           float* sumsq, void* stream);
 /* W[n, k] *= scale[k] in place (bf16) */

@@ -233,3 +233,41 @@ def test_generate_sampled_small_vs_oracle():
     agree = sum(int((got[r] == want[r]).int().cumprod(0).sum()) for r in range(4))
     print("sampled: worst oracle rank of a drawn token", worst, "| prefix agreement with the fp32-oracle draw:", agree, "/", 4 * C)
     assert worst < 20 + 4
+
+
+@pytest.mark.parametrize("R,d,F,nqkv,V", [(8, 2560, 9728, 6144, 4096), (8, 256, 512, 1024, 1024), (3, 512, 1536, 1536, 4096)])
+def test_skinny_chain_matches_single_launches(ops, R, d, F, nqkv, V):
+    """o_proj -> gate/up -> down_proj -> next qkv (or lm_head) in ONE persistent launch == the same four GEMMs launched one by one
+    (bit-exact: the stream-K reduction is fixed-order), repeated to prove the in-kernel barrier words self-reset."""
+    torch.manual_seed(d + F)
+    bf = torch.bfloat16
+    mk = lambda *s_: (torch.randn(*s_, device="cuda") * (1.0 / s_[-1] ** 0.5)).to(bf)
+    HqD = d if d < 2560 else 4096
+    w_o, w_gu, w_down, w_qkv, w_lm = mk(d, HqD), mk(2 * F, d), mk(d, F), mk(nqkv, d), mk(V, d)
+    attn = torch.randn(R, HqD, device="cuda").to(bf); h0 = torch.randn(R, d, device="cuda").to(bf)
+    n_part = ((d + 127) // 128) * 4
+    scratch = ops.skinny_scratch(max(V, 2 * F), "cuda")
+
+    def reference():
+        h = h0.clone(); ssa = torch.zeros(n_part, 32, device="cuda"); ssb = torch.zeros(n_part, 32, device="cuda")
+        x2 = ops.skinny_gemm(attn, w_o, scratch, mode=1, residual=h, sumsq_out=ssb)
+        act = ops.skinny_gemm(x2, w_gu, scratch, mode=2, sumsq_in=ssb, sumsq_in_n=n_part, eps=1e-6)
+        hn = ops.skinny_gemm(act, w_down, scratch, mode=1, residual=x2, sumsq_out=ssa)
+        qkv = ops.skinny_gemm(hn, w_qkv, scratch, sumsq_in=ssa, sumsq_in_n=n_part, eps=1e-6)
+        lg = ops.skinny_gemm(hn, w_lm, scratch, mode=3, sumsq_in=ssa, sumsq_in_n=n_part, eps=1e-6)
+        return x2, act, hn, qkv, lg
+    rx2, ract, rh, rqkv, rlg = reference()
+    for last, wlast, mode, want in (("qkv", w_qkv, 0, rqkv), ("lm_head", w_lm, 3, rlg)):
+        for rep in range(3):
+            h = h0.clone(); ssa = torch.zeros(n_part, 32, device="cuda"); ssb = torch.zeros(n_part, 32, device="cuda")
+            x2 = torch.empty(R, d, device="cuda", dtype=bf); act = torch.empty(R, F, device="cuda", dtype=bf)
+            out = torch.empty(R, wlast.shape[0], device="cuda", dtype=torch.float32 if mode == 3 else bf)
+            ops.skinny_chain([dict(x=attn, w=w_o, out=x2, mode=1, residual=h, sumsq_out=ssb),
+                              dict(x=x2, w=w_gu, out=act, mode=2, sumsq_in=ssb, sumsq_in_n=n_part),
+                              dict(x=act, w=w_down, out=h, mode=1, residual=x2, sumsq_out=ssa),
+                              dict(x=h, w=wlast, out=out, mode=mode, sumsq_in=ssa, sumsq_in_n=n_part)], R, scratch, eps=1e-6)
+            assert torch.equal(x2, rx2) and torch.equal(act, ract) and torch.equal(h, rh), f"{last} rep {rep}"
+            assert torch.equal(out, want), f"{last} rep {rep}: last phase differs"
+    # sanity of the whole chain against fp32 math
+    ref_x2 = (attn.float() @ w_o.float().T).bfloat16().float() + h0.float()
+    torch.testing.assert_close(rx2.float(), ref_x2.bfloat16().float(), rtol=2e-2, atol=2e-2)
