@@ -130,3 +130,25 @@ def chain():
         x = ops.skinny_gemm(a, w["down"], scratch, mode=1, residual=x2, sumsq_out=ssa)
 us = timed_graph(chain) / NL
 print(f"layer chain (5 launches): {us:8.2f} us per layer  -> {36 * us / 1e3:.3f} ms per token (36 layers)   PDL={'off' if os.environ.get('BR_NO_PDL') else 'on'}")
+
+# ---- the production layout: fused attention + ONE persistent chain kernel (o -> gate/up -> down -> next qkv) per layer
+b_qkv = torch.empty(R, (Hq + 2 * Hkv) * D, device=dev, dtype=bf); b_x2 = torch.empty(R, d, device=dev, dtype=bf)
+b_act = torch.empty(R, F, device=dev, dtype=bf); hbuf = x0.clone()
+def chain2():
+    for i, w in enumerate(ws_l):
+        ops.decode_attn_fused(b_qkv, qn, kn, kc, vc, table, cur, G, Hq, Hkv, D, n_shared, 8, 2, 1e6, 1e-6, wsf, attn_out, rope=rope)
+        ops.skinny_chain([dict(x=attn_out, w=w["o"], out=b_x2, mode=1, residual=hbuf, sumsq_out=ssb),
+                          dict(x=b_x2, w=w["gu"], out=b_act, mode=2, sumsq_in=ssb, sumsq_in_n=n_part),
+                          dict(x=b_act, w=w["down"], out=hbuf, mode=1, residual=b_x2, sumsq_out=ssa),
+                          dict(x=hbuf, w=ws_l[(i + 1) % NL]["qkv"], out=b_qkv, mode=0, sumsq_in=ssa, sumsq_in_n=n_part)], R, scratch, eps=1e-6)
+us = timed_graph(chain2) / NL
+print(f"layer = fused attention + persistent 4-phase GEMM chain: {us:8.2f} us per layer -> {36 * us / 1e3:.3f} ms per token; "
+      f"weight bytes {sum(v.numel() for v in ws_l[0].values()) * 2 / 1e6:.1f} MB -> {sum(v.numel() for v in ws_l[0].values()) * 2 / (us * 1e-6) / 1e9:.0f} GB/s incl. attention")
+def chain_only():
+    for i, w in enumerate(ws_l):
+        ops.skinny_chain([dict(x=attn_out, w=w["o"], out=b_x2, mode=1, residual=hbuf, sumsq_out=ssb),
+                          dict(x=b_x2, w=w["gu"], out=b_act, mode=2, sumsq_in=ssb, sumsq_in_n=n_part),
+                          dict(x=b_act, w=w["down"], out=hbuf, mode=1, residual=b_x2, sumsq_out=ssa),
+                          dict(x=hbuf, w=ws_l[(i + 1) % NL]["qkv"], out=b_qkv, mode=0, sumsq_in=ssa, sumsq_in_n=n_part)], R, scratch, eps=1e-6)
+us = timed_graph(chain_only) / NL
+print(f"persistent 4-phase GEMM chain alone: {us:8.2f} us per layer  ({sum(v.numel() for v in ws_l[0].values()) * 2 / (us * 1e-6) / 1e9:.0f} GB/s)")
