@@ -295,7 +295,9 @@ constexpr int CHAIN_MAX = 4;
 constexpr int CHAIN_THREADS = 224;           // warp 0: W producer, 1: MMA, 2-5: epilogue, 6: X producer
 
 struct ChainPhase { CUtensorMap tmW; CUtensorMap tmX; SkParams p; };
-struct ChainParams { ChainPhase ph[CHAIN_MAX]; int n_phases; int* gbar; };
+struct ChainParams { ChainPhase ph[CHAIN_MAX]; int n_phases; int* gbar; long long* dbg; };
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define CSTAMP(k) do { if (cp.dbg && et == 0) cp.dbg[(long long)blockIdx.x * 32 + (k)] = gtime(); } while (0)
 
 template <int BNX>
 __global__ void __launch_bounds__(CHAIN_THREADS, 1) skinny_chain_kernel(const __grid_constant__ ChainParams cp) {
@@ -398,11 +400,14 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) skinny_chain_kernel(const __
         // ---------------- epilogue warps 2..5 ----------------
         const int lane_grp = warp & 3;
         const int et = threadIdx.x - 64;
+        CSTAMP(0);
         br::grid_dep_wait();
+        CSTAMP(1);
         int as = 0; uint32_t aph = 0;
         for (int pi = 0; pi < nph; ++pi) {
             const SkParams& p = cp.ph[pi].p;
             const int u_lo = blockIdx.x * p.chunk, u_hi = min(p.units, u_lo + p.chunk);
+            CSTAMP(2 + pi * 6);
             if (et < 32) {                                    // per-row rstd of the folded RMSNorm (inputs complete: barrier pi-1 passed)
                 float rsv = 1.f;
                 if (p.sumsq_in && et < p.R) {
@@ -419,6 +424,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) skinny_chain_kernel(const __
                 const int seg_end = min(u_hi, (tile + 1) * p.KB);
                 const bool whole = (u == tile * p.KB) && (seg_end == (tile + 1) * p.KB);
                 br::mbar_wait(&tfull_bar[as], aph);
+                if (u == u_lo) CSTAMP(3 + pi * 6);
                 br::tc_fence_after();
                 const uint32_t taddr = tmem_base + as * BNX + ((uint32_t)(lane_grp * 32) << 16);
                 float v[BNX];
@@ -476,10 +482,12 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) skinny_chain_kernel(const __
                 }
                 u = seg_end;
             }
+            CSTAMP(4 + pi * 6);
             if (pi + 1 < nph) {
                 // grid barrier: every CTA's outputs of phase pi are globally visible before anyone loads them as phase pi+1 inputs
                 __threadfence();
                 asm volatile("bar.sync 1, 128;" ::: "memory");
+                CSTAMP(5 + pi * 6);
                 if (et == 0) {
                     atomicAdd(cp.gbar, 1);
                     const int target = (pi + 1) * (int)gridDim.x;
@@ -488,6 +496,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) skinny_chain_kernel(const __
                     *s_ready = pi + 1;
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
+                CSTAMP(6 + pi * 6);
             }
         }
         // the last CTA to finish re-zeros the barrier words for the next launch (everyone else has left the barrier code)
@@ -557,11 +566,16 @@ int br_skinny_gemm_ex(const void* X, int64_t ldx, const void* W, int64_t ldw, vo
 }
 
 
+static long long* g_chain_dbg = nullptr;
+/* profiling aid: [n_sms, 32] int64 %globaltimer stamps of the next chain launches (NULL disables) */
+int br_skinny_chain_debug(long long* buf) { g_chain_dbg = buf; return BR_OK; }
+
 int br_skinny_chain(const br_skinny_phase* phases, int n_phases, int R, float eps, void* scratch, void* stream) {
     BR_CHECK_ARG(n_phases >= 1 && n_phases <= CHAIN_MAX && R >= 1 && R <= 32 && scratch, "skinny_chain: 1..%d phases, R in [1, 32]", CHAIN_MAX);
     ChainParams cp;
     memset(&cp, 0, sizeof(cp));
     cp.n_phases = n_phases;
+    cp.dbg = g_chain_dbg;
     const int BNX = R <= 16 ? 16 : 32;
     const int grid = br_num_sms();                         // every phase uses the full grid: the barrier counts gridDim.x arrivals
     float* part = (float*)scratch;

@@ -142,6 +142,9 @@ typedef struct br_skinny_phase {
     float* sumsq_out;
 } br_skinny_phase;
 int br_skinny_chain(const br_skinny_phase* phases, int n_phases, int R, float eps, void* scratch, void* stream);
+/* profiling aid: [n_sms, 32] int64 %globaltimer stamps (per CTA: start, dep-wait, then per phase: begin, first accumulator,
+ * tiles done, barrier arrive, barrier pass) written by the next br_skinny_chain launches; NULL disables */
+int br_skinny_chain_debug(long long* buf);
 int br_embed_gather_sumsq(const int64_t* ids, const void* table, int64_t ldt, int64_t vocab, void* out, int64_t ldo, int M, int d,
                           float* sumsq, void* stream);
 /* W[n, k] *= scale[k] in place (bf16) */
