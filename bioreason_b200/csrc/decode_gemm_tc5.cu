@@ -53,7 +53,7 @@ struct SL {
     static constexpr int STAGE = A_BYTES + B_BYTES;
     static constexpr int NSTAGE = 6;        // 108 KB: two CTAs (this kernel + its PDL successor) fit one SM
     static constexpr int TILE_BYTES = NSTAGE * STAGE;
-    static constexpr int TOTAL = TILE_BYTES + 512 + 1024;   // + barriers / flags / per-row rstd + alignment slack
+    static constexpr int TOTAL = TILE_BYTES + 1024 + 1024;   // + barriers / flags / per-row rstd + alignment slack
 };
 
 // per-feature epilogue: v[r] = sum for row r of feature f
@@ -95,6 +95,34 @@ __device__ __forceinline__ void apply_epilogue(const SkParams& p, int f, int lan
             if (lane == 0) p.sumsq_out[(long long)part_row * 32 + r] = sq;
         }
     }
+}
+
+
+// Per-row rstd of the folded RMSNorm from the producer's partial sums of squares, summed in a FIXED order (reproducible) but
+// with the L2 loads spread over all 128 epilogue threads and issued in batches (a serial loop of ~80 dependent L2 round
+// trips here used to cost ~30 us per GEMM).  s_part: [4][32] floats of shared scratch.  Ends with the epilogue-group barrier.
+__device__ __forceinline__ void compute_row_rstd(const SkParams& p, int et, float* s_rs, float* s_part) {
+    const int r = et & 31, q = et >> 5;                       // row, quarter of the partial list
+    float acc = 0.f;
+    if (p.sumsq_in && r < p.R) {
+        const int n = p.sumsq_in_n;
+        const int per = (n + 3) >> 2, lo = q * per, hi = min(n, lo + per);
+        for (int i = lo; i < hi; i += 8) {
+            float t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = (i + j < hi) ? __ldcg(p.sumsq_in + (long long)(i + j) * 32 + r) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc += t[j];
+        }
+    }
+    s_part[q * 32 + r] = acc;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (et < 32) {
+        float rsv = 1.f;
+        if (p.sumsq_in && et < p.R) rsv = rsqrtf((((s_part[et] + s_part[32 + et]) + s_part[64 + et]) + s_part[96 + et]) / (float)p.K + p.eps);
+        s_rs[et] = rsv;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
 template <int BNX>
@@ -188,16 +216,7 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         const int lane_grp = warp & 3;
         const int et = threadIdx.x - 64;                      // 0..127 within the epilogue group
         br::grid_dep_wait();                                  // everything below touches data shared with earlier kernels
-        if (et < 32) {                                        // fixed-order sum of the producer's partial statistics
-            float rsv = 1.f;
-            if (p.sumsq_in && et < p.R) {
-                float acc = 0.f;
-                for (int i = 0; i < p.sumsq_in_n; ++i) acc += __ldcg(p.sumsq_in + (long long)i * 32 + et);
-                rsv = rsqrtf(acc / (float)p.K + p.eps);
-            }
-            s_rs[et] = rsv;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        compute_row_rstd(p, et, s_rs, s_rs + 32);
         int as = 0; uint32_t aph = 0;
         int u = u_lo;
         while (u < u_hi) {
@@ -408,16 +427,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) skinny_chain_kernel(const __
             const SkParams& p = cp.ph[pi].p;
             const int u_lo = blockIdx.x * p.chunk, u_hi = min(p.units, u_lo + p.chunk);
             CSTAMP(2 + pi * 6);
-            if (et < 32) {                                    // per-row rstd of the folded RMSNorm (inputs complete: barrier pi-1 passed)
-                float rsv = 1.f;
-                if (p.sumsq_in && et < p.R) {
-                    float acc = 0.f;
-                    for (int i = 0; i < p.sumsq_in_n; ++i) acc += __ldcg(p.sumsq_in + (long long)i * 32 + et);
-                    rsv = rsqrtf(acc / (float)p.K + p.eps);
-                }
-                s_rs[et] = rsv;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            compute_row_rstd(p, et, s_rs, s_rs + 32);      // inputs complete: barrier pi-1 passed
             int u = u_lo;
             while (u < u_hi) {
                 const int tile = u / p.KB;
