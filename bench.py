@@ -183,12 +183,14 @@ def run_b200(args):
     for _ in range(args.warmup):
         trainer.training_step(resident)
     trainer.timings.clear()
+    trainer.gpu_phase_ms()
     ops.LAUNCHES[0] = 0
     clocks = ClockSampler(local)
     clocks.start()
     ms = timed(args.steps, lambda: trainer.training_step(resident))
     launches = ops.LAUNCHES[0]
     phase = {k: v / args.steps for k, v in trainer.timings.items()}
+    gpu_phase = {k: v / args.steps / 1e3 for k, v in trainer.gpu_phase_ms().items()}      # CUDA-event seconds per step
 
     loss_host = torch.zeros(1).pin_memory()
 
@@ -234,7 +236,7 @@ def run_b200(args):
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     ach = bytes_k / (ms_k * 1e-3) / 1e9
     t_step = ms / args.steps / 1e3
-    decode_s = phase.get("rollout", 0.0)
+    decode_s = gpu_phase.get("rollout", phase.get("rollout", 0.0))
     dense_s = max(t_step - decode_s, 1e-9)
     roofline = {"bound": "hbm", "kernel": "skinny_tc5_kernel (decode weight streaming, %d launches = all GEMMs of one token step for the group, CUDA-graph replay)" % n_k,
                 "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 4), "traffic": None,
@@ -242,7 +244,8 @@ def run_b200(args):
                 "bytes_per_launch_avg": int(bytes_k / n_k), "launch_us_avg": round(ms_k * 1e3 / n_k, 2),
                 "phases": {"rollout_s": round(decode_s, 4), "rollout_hbm_frac": round(work["decode_bytes"] / max(decode_s, 1e-9) / 1e9 / hbm_peak, 4),
                            "dense_s": round(dense_s, 4), "dense_tensor_frac": round(work["dense_flops"] / dense_s / 1e12 / tf_peak, 4),
-                           "dense_peak_tflops": tf_peak, "host_phase_s": {k: round(v, 4) for k, v in phase.items()}}}
+                           "dense_peak_tflops": tf_peak, "gpu_phase_s": {k: round(v, 4) for k, v in gpu_phase.items()},
+                           "host_phase_s": {k: round(v, 4) for k, v in phase.items()}}}
 
     line = {"metric": "GRPO tokens/sec (rollout+update)", "value": round(tokens_per_step / t_step, 2), "unit": "tokens/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",

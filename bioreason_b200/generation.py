@@ -9,6 +9,7 @@ prefilled once and share their prompt KV pages.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -223,7 +224,9 @@ class RolloutEngine:
         b_act = torch.empty(R, F, device=dev, dtype=torch.bfloat16)
         b_logits = torch.empty(R, cfg.vocab_size, device=dev, dtype=torch.float32)
 
-        def decode_step():
+        use_chain = os.environ.get("BR_DECODE_CHAIN", "0") == "1"
+
+        def decode_step_chain():
             # 2 launches per layer: fused attention, then ONE persistent kernel running o_proj (+res) -> gate/up (folded ln2, SwiGLU)
             # -> down_proj (+res) -> the NEXT layer's qkv projection (folded ln1) / the lm_head, with grid barriers inside.
             # RMSNorm never launches: its statistics ride along in the GEMM epilogues (sum x^2 partials).
@@ -242,6 +245,23 @@ class RolloutEngine:
                                   nxt], R, scratch, eps=eps)
             sample(b_logits)
             ops.decode_advance(step, cur_len)
+
+        def decode_step_5():
+            # 5 launches per layer: qkv GEMM (folded ln1), fused attention, o_proj (+res, sum x^2), gate/up GEMM (folded ln2, SwiGLU),
+            # down_proj (+res, sum x^2); RMSNorm never launches in the decode loop.
+            ops.embed_gather_sumsq(next_ids, Wd.embed, h, ssq_e)
+            for li, Lw in enumerate(Wd.layers):
+                ops.skinny_gemm(h, Lw.w_qkv, scratch, out=b_qkv, sumsq_in=ssq_e if li == 0 else ssq_a, sumsq_in_n=1 if li == 0 else n_part, eps=eps)
+                ops.decode_attn_fused(b_qkv, Lw.q_norm, Lw.k_norm, kc[li], vc[li], table, cur_len, G, Hq, Hkv, D, n_shared, splits_shared,
+                                      splits_private, theta, eps, ws, attn_out, rope=rope)
+                ops.skinny_gemm(attn_out, Lw.w_o, scratch, mode=1, residual=h, out=b_x2, sumsq_out=ssq_b)
+                ops.skinny_gemm(b_x2, Lw.w_gu, scratch, mode=2, out=b_act, sumsq_in=ssq_b, sumsq_in_n=n_part, eps=eps)
+                ops.skinny_gemm(b_act, Lw.w_down, scratch, mode=1, residual=b_x2, out=h, sumsq_out=ssq_a)
+            ops.skinny_gemm(h, Wd.lm_head, scratch, mode=3, out=b_logits, sumsq_in=ssq_a, sumsq_in_n=n_part, eps=eps)
+            sample(b_logits)
+            ops.decode_advance(step, cur_len)
+
+        decode_step = decode_step_chain if use_chain else decode_step_5
 
         n_steps = C - 1
         graph = None

@@ -99,6 +99,30 @@ class DNALLMGRPOTrainer:
         self._gen = torch.Generator(device="cuda")
         self._gen.manual_seed(a.seed + rank)
         self.timings = defaultdict(float)
+        self._ev = []                      # (phase, start_event, end_event): GPU-side phase times, read by gpu_phase_ms()
+
+    def _mark(self, phase):
+        """Context manager: CUDA-event bracket of a phase on the current stream (no host sync)."""
+        tr = self
+
+        class _M:
+            def __enter__(self_m):
+                self_m.e0 = torch.cuda.Event(enable_timing=True); self_m.e1 = torch.cuda.Event(enable_timing=True)
+                self_m.e0.record()
+
+            def __exit__(self_m, *a):
+                self_m.e1.record()
+                tr._ev.append((phase, self_m.e0, self_m.e1))
+        return _M()
+
+    def gpu_phase_ms(self, reset=True):
+        torch.cuda.synchronize()
+        out = defaultdict(float)
+        for ph, e0, e1 in self._ev:
+            out[ph] += e0.elapsed_time(e1)
+        if reset:
+            self._ev = []
+        return dict(out)
 
     # ------------------------------------------------------------------ data
     def _get_train_sampler(self):                                                          # grpo_trainer.py:883-897
@@ -139,14 +163,16 @@ class DNALLMGRPOTrainer:
         C = self.max_completion_length
         if uniforms is None:
             uniforms = torch.rand(C, B, device=dev, generator=self._gen)
-        completion_ids = model.generate(prompt_ids, prompt_mask, mm["dna_tokenized"], mm["batch_idx_map"], uniforms=uniforms, **self.generation_kwargs)
+        with self._mark("rollout"):
+            completion_ids = model.generate(prompt_ids, prompt_mask, mm["dna_tokenized"], mm["batch_idx_map"], uniforms=uniforms, **self.generation_kwargs)
         self.timings["rollout"] += time.perf_counter() - t0
         completion_mask = ops.eos_mask(completion_ids, self.eos_token_id if not self.args.suppress_eos else -1)      # :605-609
         ids = torch.cat([prompt_ids, completion_ids], dim=1)
         attention_mask = torch.cat([prompt_mask, completion_mask.to(prompt_mask.dtype)], dim=1)                       # :612
         Cc = completion_ids.shape[1]
-        old_lp = self._get_per_token_logps(model, ids, attention_mask, keep_last=Cc, **mm) if self.num_iterations > 1 else None
-        ref_lp = self._get_per_token_logps(model, ids, attention_mask, keep_last=Cc, lora=None, **mm) if self.beta != 0.0 else None
+        with self._mark("ref_logps"):
+            old_lp = self._get_per_token_logps(model, ids, attention_mask, keep_last=Cc, **mm) if self.num_iterations > 1 else None
+            ref_lp = self._get_per_token_logps(model, ids, attention_mask, keep_last=Cc, lora=None, **mm) if self.beta != 0.0 else None
         # rewards: token-level callables f(completion_ids=, prompt_ids=, **batch) -> [B] floats (text rewards need a tokenizer)
         if rewards_per_func is None:
             rewards_per_func = torch.zeros(B, len(self.reward_funcs), device=dev)
@@ -191,7 +217,8 @@ class DNALLMGRPOTrainer:
             sl = slice(lo, hi)
             mm_c = _slice_mm(mm, lo, hi)
             t0 = time.perf_counter()
-            lp, ctx = training.policy_forward(model, ids[sl], mask[sl], mm_c["dna_tokenized"], mm_c["batch_idx_map"], C, save=backward)
+            with self._mark("policy_fwd"):
+                lp, ctx = training.policy_forward(model, ids[sl], mask[sl], mm_c["dna_tokenized"], mm_c["batch_idx_map"], C, save=backward)
             out3, dlp = ops.grpo_loss_raw(lp, old[sl] if old is not None else None, ref[sl] if ref is not None else None, adv[sl],
                                           completion_mask[sl], self.beta, self.epsilon_low, self.epsilon_high, want_grad=backward)
             w = (hi - lo) / B
@@ -199,7 +226,8 @@ class DNALLMGRPOTrainer:
             self.timings["policy_fwd"] += time.perf_counter() - t0
             if backward:
                 t0 = time.perf_counter()
-                training.policy_backward(model, ctx, dlp * (w / ga))
+                with self._mark("policy_bwd"):
+                    training.policy_backward(model, ctx, dlp * (w / ga))
                 self.timings["policy_bwd"] += time.perf_counter() - t0
         # clip_ratio is a ratio of sums; with row chunks it is weighted by rows (exact when chunks have equal mask counts)
         if self.beta > 0:
@@ -220,12 +248,15 @@ class DNALLMGRPOTrainer:
     def _optimizer_step(self):
         model = self.model
         t0 = time.perf_counter()
-        dp.allreduce_mean_([model._lora.flat_grad, model._proj_grad_w, model._proj_grad_b])     # C2: sum then / world (DDP average)
-        model.attach_grads()
-        if self.args.max_grad_norm and self.args.max_grad_norm > 0:
-            torch.nn.utils.clip_grad_norm_(model.trainable_parameters(), self.args.max_grad_norm, foreach=True)
-        self.optimizer.step()
-        model.sync_adapters(rollout=True)
+        with self._mark("grad_allreduce"):
+            dp.allreduce_mean_([model._lora.flat_grad, model._proj_grad_w, model._proj_grad_b])     # C2: sum then / world (DDP average)
+        with self._mark("optimizer"):
+            model.attach_grads()
+            if self.args.max_grad_norm and self.args.max_grad_norm > 0:
+                torch.nn.utils.clip_grad_norm_(model.trainable_parameters(), self.args.max_grad_norm, foreach=True)
+            self.optimizer.step()
+        with self._mark("adapter_sync"):
+            model.sync_adapters(rollout=True)
         self.global_step += 1
         self.timings["optimizer"] += time.perf_counter() - t0
 
