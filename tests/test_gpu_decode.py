@@ -271,3 +271,42 @@ def test_skinny_chain_matches_single_launches(ops, R, d, F, nqkv, V):
     # sanity of the whole chain against fp32 math
     ref_x2 = (attn.float() @ w_o.float().T).bfloat16().float() + h0.float()
     torch.testing.assert_close(rx2.float(), ref_x2.bfloat16().float(), rtol=2e-2, atol=2e-2)
+
+
+def test_generate_eos_and_multi_group(golden, tiny_oracle):
+    """EOS bookkeeping end to end (finished rows emit pad, output trimmed to the longest row, HF generation/utils.py:2796-2797) and a
+    batch of two different prompt groups (U=2, G=2) against the oracle loop."""
+    from bioreason_b200.configs import text_config, dna_config
+    from bioreason_b200.models import DNALLMModel
+    from oracle.generate import manual_generate
+    from oracle.models import synth_batch
+    m = DNALLMModel.from_oracle(tiny_oracle)
+    D = golden["D"]; cfg = tiny_oracle.text_config
+    # make the token greedy decoding emits at step 4 the EOS: every row of the replicated prompt stops there
+    eos = int(D["greedy"][0, 4])
+    want = manual_generate(tiny_oracle, D["batch"], max_new_tokens=12, eos_token_id=eos, pad_token_id=cfg.pad_token_id)
+    got = m.generate(**D["batch"], max_new_tokens=12, do_sample=False, eos_token_id=eos, pad_token_id=cfg.pad_token_id).cpu()
+    assert got.shape == want.shape == (4, 5) and torch.equal(got, want)
+    # ragged: rows finish at different steps -> pads after EOS, trimmed to the longest
+    rb = D["ragged_batch"]
+    base = manual_generate(tiny_oracle, rb, max_new_tokens=8)
+    eos = int(base[1, 2])
+    want, margins = manual_generate(tiny_oracle, rb, max_new_tokens=8, eos_token_id=eos, pad_token_id=cfg.pad_token_id, return_margins=True)
+    got = m.generate(**rb, max_new_tokens=8, do_sample=False, eos_token_id=eos, pad_token_id=cfg.pad_token_id).cpu()
+    assert got.shape[1] == want.shape[1]
+    _first_mismatch_ok(got, want, margins, tol=0.02)
+    # two prompt groups of G=2 (different lengths): grouping is detected, both groups prefilled once
+    tc, dc = tiny_oracle.text_config, tiny_oracle.dna_config
+    a = synth_batch(tc, dc, batch=2, n_seq=1, dna_len=9, text_len=40, seed=21, same_prompt=True)
+    b = synth_batch(tc, dc, batch=2, n_seq=1, dna_len=9, text_len=70, seed=22, same_prompt=True)
+    L = max(a["input_ids"].shape[1], b["input_ids"].shape[1])
+    def lpad(x, fill):
+        return torch.cat([torch.full((x.shape[0], L - x.shape[1]), fill, dtype=x.dtype), x], 1)
+    mix = dict(input_ids=torch.cat([lpad(a["input_ids"], tc.pad_token_id), lpad(b["input_ids"], tc.pad_token_id)]),
+               attention_mask=torch.cat([lpad(a["attention_mask"], 0), lpad(b["attention_mask"], 0)]),
+               dna_tokenized={k: torch.cat([a["dna_tokenized"][k], b["dna_tokenized"][k]]) for k in ("input_ids", "attention_mask")},
+               batch_idx_map=[0, 1, 2, 3])
+    want, margins = manual_generate(tiny_oracle, mix, max_new_tokens=6, return_margins=True)
+    got, st = m.generate(**mix, max_new_tokens=6, do_sample=False, return_stats=True)
+    assert st["G"] == 2 and st["unique_prompts"] == 2
+    _first_mismatch_ok(got.cpu(), want, margins, tol=0.02)
