@@ -16,7 +16,7 @@ using namespace attn;
 namespace {
 
 __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-#define STAMP(k) do { if (p.dbg && tid == 0) p.dbg[(long long)blockIdx.x * 8 + (k)] = gtime(); } while (0)
+#define STAMP(k) do { if (p.dbg && tid == 0) p.dbg[(long long)blockIdx.x * 16 + (k)] = gtime(); } while (0)
 
 __device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
@@ -31,7 +31,7 @@ struct FusedParams {
     float* part_o; float* part_lse; int* counters;      // [R,Hq,n_slots,D], [R,Hq,n_slots], [R*Hkv]
     bf16* out; long long ldo;
     float scale_log2, theta, eps;
-    long long* dbg;                      // optional [items, 8] globaltimer stamps (profiling aid)
+    long long* dbg;                      // optional [items, 16] globaltimer stamps (profiling aid)
     const float2* rope;                  // [n_pos, D/2] (cos, sin), bf16-rounded like HF's tables; may be null (computed inline)
     int rope_n_pos;
 };
@@ -176,6 +176,8 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
                 posv[i] = __ldcg(p.cur_len + row);
             }
         }
+        if (p.dbg && (rl[0].x ^ rl[3].w ^ (uint32_t)posv[3]) == 0x12345u) STAMP(15);      // (forces the loads to have landed before stamp 8)
+        STAMP(8);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int s = warp * 16 + i * 4 + q4;
@@ -191,6 +193,7 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
             *reinterpret_cast<uint4*>(tile_ptr<D>(sQ, s, 8 + sub)) = pack8(hi);
         }
     }
+    STAMP(9);
     // ---- append the new token's K / V (private item that owns the newest page)
     if (!shared_pass) {
         const int pos = kv_len - 1;

@@ -186,7 +186,7 @@ int br_decode_attn_fused(const void* qkv_raw, int64_t ld, const void* q_norm_w, 
                          void* stream);
 /* rope_table [n_pos, head_dim/2, 2] f32 = (cos, sin) rounded to bf16 precision (HF builds its tables in the model dtype);
  * optional input of br_decode_attn_fused: removes powf/sincosf from the decode loop. */
-/* profiling aid: per-item phase timestamps ([items, 8] int64, %globaltimer ns) for the next fused-attention launches */
+/* profiling aid: per-item phase timestamps ([items, 16] int64, %globaltimer ns) for the next fused-attention launches */
 int br_decode_attn_fused_debug(long long* buf);
 int br_rope_table(float* out, int n_pos, int head_dim, float theta, void* stream);
 

@@ -78,7 +78,7 @@ for ss, sp in ((8, 2), (16, 2), (8, 4), (4, 1)):
 # phase timestamps of one fused-attention launch
 from bioreason_b200._lib import lib as _lib, ffi as _ffi
 items = 64 + 128
-dbg = torch.zeros(items, 8, dtype=torch.int64, device=dev)
+dbg = torch.zeros(items, 16, dtype=torch.int64, device=dev)
 _lib().br_decode_attn_fused_debug(_ffi.cast("long long*", dbg.data_ptr()))
 wsf = ops.decode_fused_workspace(R, Hq, Hkv, D, 10, dev); out = torch.empty(R, Hq * D, device=dev, dtype=bf)
 for _ in range(3):
@@ -87,7 +87,7 @@ torch.cuda.synchronize()
 _lib().br_decode_attn_fused_debug(_ffi.NULL)
 t = dbg.double().cpu(); t0 = t[:, 0].min()
 rel = (t - t0) / 1e3
-names = ["start", "dep_wait", "q_prep", "tile0", "tiles", "partials", "counter", "end"]
+names = ["start", "dep_wait", "q_prep", "tile0", "tiles", "partials", "counter", "end", "q_loaded", "q_roped"]
 for lab, sl in (("shared", slice(0, 64)), ("private", slice(64, 192))):
     print(f"fused attention phases ({lab}, us since first CTA start): " + "  ".join(f"{n}={rel[sl, i].mean():.1f}/{rel[sl, i].max():.1f}" for i, n in enumerate(names)))
 
