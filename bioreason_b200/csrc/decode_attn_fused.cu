@@ -108,6 +108,23 @@ __device__ __forceinline__ void norm_rope_q8(float (&lo)[8], float (&hi)[8], con
         hi[e] = rbf(b * cs) + rbf(a * sn);
     }
 }
+// same arithmetic with the cos/sin pairs and the norm weights already in registers (all loads hoisted by the caller)
+template <int D>
+__device__ __forceinline__ void norm_rope_q8_pre(float (&lo)[8], float (&hi)[8], const float (&wl)[8], const float (&wh)[8], const float2 (&cs_sn)[8],
+                                                 float eps) {
+    float ss = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ss += lo[e] * lo[e] + hi[e] * hi[e];
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+    const float rstd = rsqrtf(ss / (float)D + eps);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float a = rbf(wl[e] * rbf(lo[e] * rstd)), b = rbf(wh[e] * rbf(hi[e] * rstd));
+        const float cs = cs_sn[e].x, sn = cs_sn[e].y;
+        lo[e] = rbf(a * cs) + rbf(-b * sn);
+        hi[e] = rbf(b * cs) + rbf(a * sn);
+    }
+}
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
     const float2 a = br::unpack_bf16(v.x), b = br::unpack_bf16(v.y), c = br::unpack_bf16(v.z), d = br::unpack_bf16(v.w);
     f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
@@ -176,15 +193,30 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
                 posv[i] = __ldcg(p.cur_len + row);
             }
         }
-        if (p.dbg && (rl[0].x ^ rl[3].w ^ (uint32_t)posv[3]) == 0x12345u) STAMP(15);      // (forces the loads to have landed before stamp 8)
+        // norm weights and (when the table covers every position) the cos/sin pairs of all 4 passes are fetched up front too
+        float wl[8], wh[8];
+        { uint4 a = __ldg(reinterpret_cast<const uint4*>(p.qw + sub * 8)), b = __ldg(reinterpret_cast<const uint4*>(p.qw + 64 + sub * 8)); unpack8(a, wl); unpack8(b, wh); }
+        bool table_ok = p.rope != nullptr;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) table_ok &= (posv[i] < p.rope_n_pos);
+        table_ok = __all_sync(0xffffffffu, table_ok);               // warp-uniform: the shuffles below use the full mask
+        float2 tcs[4][8];
+        if (table_ok) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4* tp = reinterpret_cast<const float4*>(p.rope + (long long)(posv[i] < 0 ? 0 : posv[i]) * (D / 2) + sub * 8);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float4 t4 = __ldg(tp + e); tcs[i][2 * e] = make_float2(t4.x, t4.y); tcs[i][2 * e + 1] = make_float2(t4.z, t4.w); }
+            }
+        }
         STAMP(8);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int s = warp * 16 + i * 4 + q4;
             float lo[8], hi[8];
             unpack8(rl[i], lo); unpack8(rh[i], hi);
-            // all 8 lanes of a vector take the same branch; shuffles inside use the full mask, so keep the warp converged
-            norm_rope_q8<D>(lo, hi, p.qw, posv[i] < 0 ? 0 : posv[i], sub, p.theta, p.eps, p.rope, p.rope_n_pos);
+            if (table_ok) norm_rope_q8_pre<D>(lo, hi, wl, wh, tcs[i], p.eps);
+            else norm_rope_q8<D>(lo, hi, p.qw, posv[i] < 0 ? 0 : posv[i], sub, p.theta, p.eps, p.rope, p.rope_n_pos);
             if (posv[i] < 0) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) lo[e] = hi[e] = 0.f;
