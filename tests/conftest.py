@@ -10,6 +10,13 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """Make sure libbioreason_b200.so matches the sources (hash-checked, a no-op when up to date)."""
+    from bioreason_b200 import build
+    build.build()
+
+
 @pytest.fixture(scope="session")
 def golden():
     import torch
