@@ -236,6 +236,11 @@ class DNALLMModel(nn.Module):
         n = (tgt >= 0).sum().clamp(min=1)
         return -(logp.sum() / n)
 
+    def sft_step(self, input_ids, attention_mask, dna_tokenized=None, batch_idx_map=None, labels=None, backward: bool = True):
+        """SFT loss (+ hand-written backward into the LoRA / projector gradient buffers); see training.sft_step."""
+        from .. import training
+        return training.sft_step(self, input_ids, attention_mask, dna_tokenized, batch_idx_map, labels, backward=backward)
+
     def per_token_logps(self, input_ids, attention_mask, dna_tokenized=None, batch_idx_map=None, keep_last: Optional[int] = None):
         """Fused equivalent of `_get_per_token_logps` (grpo_trainer.py:510-520): [B, L-1] (or the last `keep_last`
         columns, i.e. the `[:, P-1:]` slice the trainer takes) log-probs of the realised next tokens; no [B, L, V]."""

@@ -20,8 +20,10 @@ class PolicyCtx:
 
 
 def policy_forward(model, input_ids, attention_mask, dna_tokenized, batch_idx_map, keep_last: int, *, save: bool = True,
-                   lora="policy") -> "tuple[torch.Tensor, Optional[PolicyCtx]]":
-    """Returns (logps [B, keep_last] fp32, ctx).  lora: "policy" (adapters on), None (base weights = reference policy)."""
+                   lora="policy", targets: Optional[torch.Tensor] = None) -> "tuple[torch.Tensor, Optional[PolicyCtx]]":
+    """Returns (logps [B, keep_last] fp32, ctx).  lora: "policy" (adapters on), None (base weights = reference policy).
+    targets: optional [B, keep_last] class ids scored at the last keep_last positions before the end (default: the realised next
+    tokens input_ids[:, L-keep_last:]); entries < 0 are ignored (log-prob 0, no gradient) -- the SFT label mask."""
     W = model._dec
     dev = W.embed.device
     input_ids = input_ids.to(dev)
@@ -51,7 +53,7 @@ def policy_forward(model, input_ids, attention_mask, dna_tokenized, batch_idx_ma
     cols = torch.arange(L - 1 - n, L - 1, device=dev)
     rows = (torch.arange(B, device=dev)[:, None] * L + cols[None, :]).reshape(-1).to(torch.int32)
     h_sel = ops.gather_rows(hn, rows)
-    tgt = input_ids[:, L - n:].reshape(-1).to(torch.int32)
+    tgt = (input_ids[:, L - n:] if targets is None else targets.to(dev)).reshape(-1).to(torch.int32)
     logp, lse = ops.lmhead_logprob(h_sel, W.lm_head, tgt)
     ctx = None
     if save:
@@ -157,6 +159,22 @@ def policy_backward(model, ctx: PolicyCtx, dlogp: torch.Tensor):
         model._proj_grad_w.add_(gw)
         ops.colsum_accumulate_(model._proj_grad_b, dE)
     return dh
+
+
+def sft_step(model, input_ids, attention_mask, dna_tokenized, batch_idx_map, labels, *, backward: bool = True, grad_scale: float = 1.0):
+    """One supervised step (train_dna_qwen.py:179-213 -> HF ForCausalLMLoss, loss/loss_utils.py:28-67): shift, ignore -100, mean CE.
+    Returns the loss; with backward=True accumulates d(loss * grad_scale) into the LoRA / projector gradient buffers."""
+    dev = model._dec.embed.device
+    labels = labels.to(dev)
+    B, L = labels.shape
+    tgt = torch.where(labels[:, 1:] == -100, torch.full_like(labels[:, 1:], -1), labels[:, 1:])           # position t predicts label t+1
+    valid = tgt >= 0
+    n = valid.sum().clamp(min=1).float()
+    lp, ctx = policy_forward(model, input_ids, attention_mask, dna_tokenized, batch_idx_map, L - 1, save=backward, targets=tgt)
+    loss = -(lp * valid).sum() / n
+    if backward:
+        policy_backward(model, ctx, (-(valid.float()) / n) * grad_scale)
+    return loss
 
 
 class _PolicyLogps(torch.autograd.Function):

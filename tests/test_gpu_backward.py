@@ -189,3 +189,42 @@ def test_policy_gradients_vs_oracle(cfg_name, B, n_seq, dna_len, text_len, C):
     assert _rel(m.dna_projection.weight.grad.cpu(), oracle.dna_projection.weight.grad) < 0.05
     p0 = lora.params[0]
     assert _rel(p0.grad.cpu(), onames[[n for n, q in m.text_model.named_parameters() if q is p0][0]].grad) < 0.08
+
+
+def test_sft_step_vs_oracle():
+    """Config (b) shape of work: CE loss over assistant-span labels + backward through LoRA and the projector vs torch autograd."""
+    from bioreason_b200.configs import text_config, dna_config
+    from bioreason_b200.models import DNALLMModel
+    from oracle.models import build_oracle, synth_batch
+    from oracle import lora as olora
+    tc, dc = text_config("small"), dna_config("small")
+    oracle = build_oracle(tc, dc, seed=13)
+    batch = synth_batch(tc, dc, batch=3, n_seq=2, dna_len=[30, 22, 30], text_len=[64, 50, 71], seed=6)
+    labels = batch["input_ids"].clone()
+    labels[batch["attention_mask"] == 0] = -100
+    labels[:, : labels.shape[1] - 24] = -100                               # only the last 24 tokens ("assistant span") are scored
+    m = DNALLMModel.from_oracle(oracle)
+    lora = m.enable_lora(r=16, alpha=32.0, seed=1)
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(2)
+        for p in lora.params[1::2]:
+            p.copy_((torch.randn(p.shape, generator=g) * 0.02).to(p.device))
+    m.sync_adapters(rollout=False)
+    olora.inject(oracle.text_model, 16, 32.0)
+    sd = {k: v.detach().float().cpu() for k, v in m.text_model.state_dict().items() if "lora_" in k}
+    assert not oracle.text_model.load_state_dict(sd, strict=False).unexpected_keys
+    for p in oracle.dna_projection.parameters():
+        p.requires_grad_(True)
+    out = oracle(**batch, labels=labels)
+    out.loss.backward()
+    m.zero_grad_buffers()
+    loss = m.sft_step(**batch, labels=labels)
+    assert abs(loss.item() - out.loss.item()) < 5e-3, (loss.item(), out.loss.item())
+    # forward-only .loss of the drop-in forward() agrees too
+    assert abs(m(**batch, labels=labels).loss.item() - out.loss.item()) < 5e-3
+    m.attach_grads()
+    onames = dict(oracle.text_model.named_parameters())
+    worst = max(_rel(p.grad.cpu(), onames[n].grad) for n, p in m.text_model.named_parameters() if "lora_" in n)
+    rw = _rel(m.dna_projection.weight.grad.cpu(), oracle.dna_projection.weight.grad)
+    print(f"sft: loss {loss.item():.4f} vs {out.loss.item():.4f}; worst LoRA grad rel err {worst:.4f}; projector dW {rw:.4f}")
+    assert worst < 0.08 and rw < 0.05
