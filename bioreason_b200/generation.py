@@ -191,6 +191,13 @@ class RolloutEngine:
         scratch = ops.skinny_scratch(max(cfg.vocab_size, 2 * cfg.intermediate_size), dev)
         splits_shared = min(8, n_shared) if n_shared > 0 else 0
         splits_private = 2 if n_shared > 0 else 8
+        cap = 3 * torch.cuda.get_device_properties(dev).multi_processor_count      # the fused kernel's merger items need co-residency
+        n_items = lambda ss, sp: (R // G) * Hkv * ss + R * Hkv * sp
+        while n_items(splits_shared, splits_private) > cap and (splits_shared > 1 or splits_private > 1):
+            if splits_private > 1 and (splits_private >= splits_shared or splits_shared <= 1):
+                splits_private //= 2
+            else:
+                splits_shared = max(1, splits_shared // 2)
         if G * (Hq // Hkv) > 32:
             raise NotImplementedError("fused decode attention handles G * Hq/Hkv <= 32 query vectors per kv head")
         n_slots = splits_shared + splits_private
