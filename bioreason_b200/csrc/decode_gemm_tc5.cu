@@ -136,8 +136,8 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     uint64_t* tfull_bar = empty_bar + L::NSTAGE;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);      // [2]
-    float* s_rs = reinterpret_cast<float*>(s_flag + 2);       // [32] per-row rstd of the folded RMSNorm (+[128] scratch)
+    int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
+    float* s_rs = reinterpret_cast<float*>(s_flag + 1);       // [32] per-row rstd of the folded RMSNorm
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int u_lo = blockIdx.x * p.chunk;
@@ -219,10 +219,6 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         compute_row_rstd(p, et, s_rs, s_rs + 32);
         int as = 0; uint32_t aph = 0;
         int u = u_lo;
-        // A CTA's chunk covers at most two PARTIAL tiles (its first and its last); both partials are published first and the
-        // (up to two) fixed-order reductions run afterwards, so a CTA that is the last arriver for both does not serialise
-        // two publish -> fence -> count -> reduce round trips (that was the longest tail of the launch).
-        int pend_tile[2]; int n_pend = 0;
         while (u < u_hi) {
             const int tile = u / p.KB;
             const int seg_end = min(u_hi, (tile + 1) * p.KB);
@@ -244,53 +240,48 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             __syncwarp();
             if (lane == 0) br::mbar_arrive(&tempty_bar[as]);   // accumulator drained into registers
             if (++as == 2) { as = 0; aph ^= 1; }
+            const int f = tile * BM + lane_grp * 32 + lane;
+            const int part_row = tile * 4 + lane_grp;
             if (whole) {
-                apply_epilogue<BNX>(p, tile * BM + lane_grp * 32 + lane, lane, v, s_rs, tile * 4 + lane_grp);
+                apply_epilogue<BNX>(p, f, lane, v, s_rs, part_row);
             } else {
+                // deterministic stream-K: write this CTA's partial tile to its own scratch slot; the last arriver adds the
+                // partials of the contributing CTAs in ascending CTA order (no floating-point atomics anywhere)
+                const int first_c = (tile * p.KB) / p.chunk, last_c = ((tile + 1) * p.KB - 1) / p.chunk;
                 const int my_slot = (tile == u_lo / p.KB) ? 0 : 1;
                 float* mine = p.scratch + (((long long)blockIdx.x * 2 + my_slot) * BNX) * BM + lane_grp * 32 + lane;
 #pragma unroll
                 for (int r = 0; r < BNX; ++r)
                     if (r < p.R) __stcg(mine + r * BM, v[r]);
-                pend_tile[n_pend++] = tile;
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) *s_flag = (atomicAdd(p.counters + tile, 1) == last_c - first_c);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (*s_flag) {
+                    __threadfence();
+#pragma unroll
+                    for (int r = 0; r < BNX; ++r) v[r] = 0.f;
+                    for (int c0 = first_c; c0 <= last_c; c0 += 4) {             // 4 contributors' loads in flight at a time
+                        float t[4][BNX];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int c = c0 + j;
+                            const int slot = (tile == (c * p.chunk) / p.KB) ? 0 : 1;
+                            const float* src = p.scratch + (((long long)c * 2 + slot) * BNX) * BM + lane_grp * 32 + lane;
+#pragma unroll
+                            for (int r = 0; r < BNX; ++r) t[j][r] = (c <= last_c && r < p.R) ? __ldcg(src + r * BM) : 0.f;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+#pragma unroll
+                            for (int r = 0; r < BNX; ++r) v[r] += t[j][r];                  // ascending CTA order: deterministic
+                    }
+                    if (et == 0) p.counters[tile] = 0;
+                    apply_epilogue<BNX>(p, f, lane, v, s_rs, part_row);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");     // s_flag reusable
             }
             u = seg_end;
-        }
-        if (n_pend) {                                           // block-uniform
-            __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (et < n_pend) {
-                const int tile = pend_tile[et];
-                const int first_c = (tile * p.KB) / p.chunk, last_c = ((tile + 1) * p.KB - 1) / p.chunk;
-                s_flag[et] = (atomicAdd(p.counters + tile, 1) == last_c - first_c);
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int k = 0; k < n_pend; ++k) {
-                if (!s_flag[k]) continue;                       // block-uniform
-                const int tile = pend_tile[k];
-                const int first_c = (tile * p.KB) / p.chunk, last_c = ((tile + 1) * p.KB - 1) / p.chunk;
-                __threadfence();
-                float v[BNX];
-#pragma unroll
-                for (int r = 0; r < BNX; ++r) v[r] = 0.f;
-                for (int c0 = first_c; c0 <= last_c; c0 += 4) {             // 4 contributors' loads in flight at a time
-                    float t[4][BNX];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int c = c0 + j;
-                        const int slot = (tile == (c * p.chunk) / p.KB) ? 0 : 1;
-                        const float* src = p.scratch + (((long long)c * 2 + slot) * BNX) * BM + lane_grp * 32 + lane;
-#pragma unroll
-                        for (int r = 0; r < BNX; ++r) t[j][r] = (c <= last_c && r < p.R) ? __ldcg(src + r * BM) : 0.f;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-#pragma unroll
-                        for (int r = 0; r < BNX; ++r) v[r] += t[j][r];                  // ascending CTA order: deterministic
-                }
-                if (et == 0) p.counters[tile] = 0;
-                apply_epilogue<BNX>(p, tile * BM + lane_grp * 32 + lane, lane, v, s_rs, tile * 4 + lane_grp);
-            }
         }
     }
     br::tc_fence_before();
