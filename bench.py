@@ -131,6 +131,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from bioreason_b200.build import ensure_built
+    ensure_built()                                                         # the .so normally travels with the tree; build it if it does not
     from bioreason_b200 import ops
     from bioreason_b200.configs import dna_config, text_config
     from bioreason_b200.models import DNALLMModel

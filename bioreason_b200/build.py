@@ -86,5 +86,21 @@ def build(verbose: bool = False, force: bool = False) -> str:
     return LIB
 
 
+def ensure_built() -> str:
+    """Build once if the shared object is missing (safe under torchrun: an exclusive lock file serialises the ranks)."""
+    if os.path.exists(LIB):
+        return LIB
+    import fcntl
+    os.makedirs(OUT_DIR, exist_ok=True)
+    with open(os.path.join(OUT_DIR, ".build.lock"), "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            if not os.path.exists(LIB):
+                build()
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
+    return LIB
+
+
 if __name__ == "__main__":
     build(verbose=True, force="--force" in sys.argv)
