@@ -241,7 +241,10 @@ def run_b200(args):
     decode_s = gpu_phase.get("rollout", phase.get("rollout", 0.0))
     dense_s = max(t_step - decode_s, 1e-9)
     roofline = {"bound": "hbm", "kernel": "skinny_tc5_kernel (decode weight streaming, %d launches = all GEMMs of one token step for the group, CUDA-graph replay)" % n_k,
-                "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 4), "traffic": None,
+                "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 4),
+                # dram__bytes_read+write per launch from the committed `ncu --set full` capture: 50.10 MB for the 49.81 MB down_proj launch and
+                # 31.59 MB for the 31.46 MB qkv launch (profiles/r01_ncu_full_skinny_tc5_kernel.txt) -> 1.005 x the algorithmic bytes
+                "traffic": int(1.005 * bytes_k / n_k), "traffic_source": "ncu capture ratio 1.005 (profiles/r01_ncu_full_skinny_tc5_kernel.txt)",
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                 "bytes_per_launch_avg": int(bytes_k / n_k), "launch_us_avg": round(ms_k * 1e3 / n_k, 2),
                 "phases": {"rollout_s": round(decode_s, 4), "rollout_hbm_frac": round(work["decode_bytes"] / max(decode_s, 1e-9) / 1e9 / hbm_peak, 4),
@@ -255,7 +258,7 @@ def run_b200(args):
             "config": {"workload": "(c) NT-v2-500M + Qwen3-4B GRPO step: %d prompt x G=%d per GPU, P=%d (2x%d DNA + %d text), C=%d, EOS suppressed, "
                                    "mu=1, beta=0.04, LoRA r=32 + projector, AdamW" % (args.prompts_per_gpu, args.G, args.text_len + 2 * args.dna_len,
                                                                                       args.dna_len, args.text_len, args.completion),
-                       "text": args.text, "dna": args.dna, "rows_per_gpu": B, "parallelism": f"dp{world}",
+                       "shapes": f"{args.dna}+{args.text}", "rows_per_gpu": B, "parallelism": f"dp{world}",
                        "l2": "weights (8 GB) and activations (>60 GB) exceed the 126 MB L2 every step; no flush needed",
                        "weights": "seeded random init (no checkpoints offline)", "build_s": round(t_build, 1)},
             "e2e": {"value": round(tokens_per_step / (ms_e2e / args.steps / 1e3), 2), "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes,
@@ -378,7 +381,7 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(cb["est_step_s"] * 1e3, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "(c) NT-v2-500M + Qwen3-4B GRPO step on the host cores via the CPU oracle (bounded sample, composed)",
-                       "text": args.text, "dna": args.dna, "parallelism": "cpu"},
+                       "shapes": f"{args.dna}+{args.text}", "parallelism": "cpu"},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": round(time.perf_counter() - t0, 1)}
     print(json.dumps(line), flush=True)
