@@ -102,6 +102,12 @@ def make_prompt_batch(tc, dc, args, seed):
     return out
 
 
+def workload_string(args):
+    return ("(c) NT-v2-500M + Qwen3-4B GRPO step: %d prompt x G=%d per GPU, P=%d (2x%d DNA + %d text), C=%d, EOS suppressed, "
+            "mu=1, beta=0.04, LoRA r=32 + projector, AdamW" % (args.prompts_per_gpu, args.G, args.text_len + 2 * args.dna_len,
+                                                               args.dna_len, args.text_len, args.completion))
+
+
 def algorithmic_work(tc, dc, args):
     """SURVEY.md §8d A_min: FLOPs of the dense phases and HBM bytes of the decode phase, per GPU per step."""
     d, F, V, nl = tc.hidden_size, tc.intermediate_size, tc.vocab_size, tc.num_hidden_layers
@@ -255,9 +261,7 @@ def run_b200(args):
     line = {"metric": "GRPO tokens/sec (rollout+update)", "value": round(tokens_per_step / t_step, 2), "unit": "tokens/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "(c) NT-v2-500M + Qwen3-4B GRPO step: %d prompt x G=%d per GPU, P=%d (2x%d DNA + %d text), C=%d, EOS suppressed, "
-                                   "mu=1, beta=0.04, LoRA r=32 + projector, AdamW" % (args.prompts_per_gpu, args.G, args.text_len + 2 * args.dna_len,
-                                                                                      args.dna_len, args.text_len, args.completion),
+            "config": {"workload": workload_string(args),
                        "shapes": f"{args.dna}+{args.text}", "rows_per_gpu": B, "parallelism": f"dp{world}",
                        "l2": "weights (8 GB) and activations (>60 GB) exceed the 126 MB L2 every step; no flush needed",
                        "weights": "seeded random init (no checkpoints offline)", "build_s": round(t_build, 1)},
@@ -380,7 +384,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "GRPO tokens/sec (rollout+update)", "value": cb["value"], "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(cb["est_step_s"] * 1e3, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "(c) NT-v2-500M + Qwen3-4B GRPO step on the host cores via the CPU oracle (bounded sample, composed)",
+            "config": {"workload": workload_string(args), "how": "host cores via the CPU oracle: bounded sample at real widths, composed with the reference schedule",
                        "shapes": f"{args.dna}+{args.text}", "parallelism": "cpu"},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": round(time.perf_counter() - t0, 1)}
