@@ -49,3 +49,20 @@ def test_sass_is_blackwell_native(built_lib):
     sass = subprocess.run([cuobjdump, "-sass", obj], capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
         assert mnemonic in sass, mnemonic
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline leg may touch it."""
+    import re
+    bad = []
+    for base in ("bioreason_b200", "compat"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith(".py"):
+                    src = open(os.path.join(dirpath, f)).read()
+                    if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M):
+                        bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    b200_arm = bench[bench.index("def run_b200"):bench.index("# CPU reference arm")]
+    assert "oracle" not in b200_arm.replace("oracle's", "")           # the timed arm is oracle-free
