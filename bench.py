@@ -175,15 +175,19 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(n, fn):
+    per_step = {}
+
+    def timed(n, fn, tag=None):
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        evs[0].record()
+        for i in range(n):
             fn()
-        e1.record()
+            evs[i + 1].record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if tag:
+            per_step[tag] = [round(evs[i].elapsed_time(evs[i + 1]), 1) for i in range(n)]
+        ms = torch.tensor([evs[0].elapsed_time(evs[n])], device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
@@ -195,7 +199,7 @@ def run_b200(args):
     ops.LAUNCHES[0] = 0
     clocks = ClockSampler(local)
     clocks.start()
-    ms = timed(args.steps, lambda: trainer.training_step(resident))
+    ms = timed(args.steps, lambda: trainer.training_step(resident), tag="resident")
     launches = ops.LAUNCHES[0]
     phase = {k: v / args.steps for k, v in trainer.timings.items()}
     gpu_phase = {k: v / args.steps / 1e3 for k, v in trainer.gpu_phase_ms().items()}      # CUDA-event seconds per step
@@ -205,7 +209,7 @@ def run_b200(args):
     def e2e_step():
         loss = trainer.training_step(to_device())                        # H2D of this step's inputs from pinned memory
         loss_host.copy_(loss.detach().reshape(1), non_blocking=False)    # D2H read of the step's result
-    ms_e2e = timed(args.steps, e2e_step)
+    ms_e2e = timed(args.steps, e2e_step, tag="e2e")
     clk = clocks.stop()
 
     # ---- roofline of the dominant kernel: the decode weight-streaming GEMM, timed alone with CUDA events (weights of all
@@ -267,7 +271,9 @@ def run_b200(args):
                        "weights": "seeded random init (no checkpoints offline)", "build_s": round(t_build, 1)},
             "e2e": {"value": round(tokens_per_step / (ms_e2e / args.steps / 1e3), 2), "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
+            "step_ms": per_step, "mem_gb": {"max_allocated": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
+                                            "max_reserved": round(torch.cuda.max_memory_reserved() / 2 ** 30, 1)}}
     if rank == 0 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_reference(args, budget_s=args.cpu_budget_s)
