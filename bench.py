@@ -194,6 +194,8 @@ def run_b200(args):
 
     for _ in range(args.warmup):
         trainer.training_step(resident)
+    import gc
+    gc.collect(); gc.freeze(); gc.disable()                               # no collector pauses inside the timed regions (host jitter)
     trainer.timings.clear()
     trainer.gpu_phase_ms()
     ops.LAUNCHES[0] = 0
