@@ -276,7 +276,7 @@ def run_b200(args):
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
             "step_ms": per_step, "mem_gb": {"max_allocated": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
                                             "max_reserved": round(torch.cuda.max_memory_reserved() / 2 ** 30, 1)}}
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:              # the CPU baseline is timed at N=1 only
         try:
             line["cpu_baseline"] = cpu_reference(args, budget_s=args.cpu_budget_s)
         except Exception as e:                                            # the baseline must never take the measurement down
