@@ -11,6 +11,7 @@ from __future__ import annotations
 import math
 import os
 from dataclasses import dataclass
+from types import SimpleNamespace
 from typing import List, Optional
 
 import torch
@@ -85,6 +86,7 @@ class RolloutEngine:
         self._graph = None
         self._graph_key = None
         self._weights = None            # DecoderW used for the rollout (base, or base+LoRA merged)
+        self._cached = {}               # rollout shape key -> static buffers + captured decode graph (reused across steps)
 
     # ------------------------------------------------------------------
     def rollout_weights(self) -> DecoderW:
@@ -151,11 +153,23 @@ class RolloutEngine:
                 table[r, n_shared:n_shared + priv_pages[u]] = torch.tensor(mine, dtype=torch.int32)
             prefill_pages.append(table[u * G, :math.ceil(plen[u] / PAGE)].clone())
         n_pages = next_page
-        table = table.to(dev)
+        table_host = table
         nl = len(W.layers)
-        kc = torch.empty(nl, n_pages, Hkv, PAGE, D, device=dev, dtype=torch.bfloat16)
-        vc = torch.empty_like(kc)
-        pp_dev = [p.to(dev) for p in prefill_pages]
+        # Static buffers + the captured decode graph are cached per rollout shape: a training run replays the same graph every
+        # step (no per-step capture, no graph-pool / allocator churn -- that churn showed up as multi-second host stalls).
+        key = (B, G, tuple(plen), C, n_shared, max_pages, n_pages, params.do_sample, params.temperature, params.top_k, params.top_p,
+               params.eos_token_id, params.pad_token_id, id(Wd), bool(use_graph), os.environ.get("BR_DECODE_CHAIN", "0"))
+        St = self._cached.get(key)
+        hit = St is not None
+        if not hit:
+            if len(self._cached) >= 4:
+                self._cached.clear()
+            St = SimpleNamespace()
+            St.table = table.to(dev)
+            St.kc = torch.empty(nl, n_pages, Hkv, PAGE, D, device=dev, dtype=torch.bfloat16)
+            St.vc = torch.empty_like(St.kc)
+            St.pp_dev = [p.to(dev) for p in prefill_pages]
+        table, kc, vc, pp_dev = St.table, St.kc, St.vc, St.pp_dev
 
         def kv_sink(li, qkv):
             for u in range(U):
@@ -170,47 +184,61 @@ class RolloutEngine:
                 n_tail = math.ceil(plen[u] / PAGE) - n_shared
                 for j in range(n_tail):
                     for gidx in range(1, G):
-                        src.append(int(prefill_pages[u][n_shared + j])); dst.append(int(table[u * G + gidx, n_shared + j]))
+                        src.append(int(prefill_pages[u][n_shared + j])); dst.append(int(table_host[u * G + gidx, n_shared + j]))
             if src:
                 s_t, d_t = torch.tensor(src, device=dev), torch.tensor(dst, device=dev)
                 kc[:, d_t] = kc[:, s_t]; vc[:, d_t] = vc[:, s_t]
 
         # ---- decode state
         R = B
-        tokens = torch.full((R, C), params.pad_token_id if params.pad_token_id is not None else 0, device=dev, dtype=torch.int64)
-        next_ids = torch.zeros(R, device=dev, dtype=torch.int64)
-        finished = torch.zeros(R, device=dev, dtype=torch.int32)
-        step = torch.zeros(1, device=dev, dtype=torch.int32)
-        cur_len = torch.tensor([plen[r // G] for r in range(R)], device=dev, dtype=torch.int32)
+        eos = params.eos_token_id if params.eos_token_id is not None else -1
+        pad_fill = params.pad_token_id if params.pad_token_id is not None else 0
         if params.do_sample:
             if uniforms is None:
                 uniforms = torch.rand(C, R, device=dev, dtype=torch.float32)
             uniforms = uniforms.to(dev).float().contiguous()
             assert uniforms.shape == (C, R)
-        eos = params.eos_token_id if params.eos_token_id is not None else -1
-        scratch = ops.skinny_scratch(max(cfg.vocab_size, 2 * cfg.intermediate_size), dev)
-        splits_shared = min(8, n_shared) if n_shared > 0 else 0
-        splits_private = 2 if n_shared > 0 else 8
-        cap = 3 * torch.cuda.get_device_properties(dev).multi_processor_count      # the fused kernel's merger items need co-residency
-        n_items = lambda ss, sp: (R // G) * Hkv * ss + R * Hkv * sp
-        while n_items(splits_shared, splits_private) > cap and (splits_shared > 1 or splits_private > 1):
-            if splits_private > 1 and (splits_private >= splits_shared or splits_shared <= 1):
-                splits_private //= 2
-            else:
-                splits_shared = max(1, splits_shared // 2)
-        if G * (Hq // Hkv) > 32:
-            raise NotImplementedError("fused decode attention handles G * Hq/Hkv <= 32 query vectors per kv head")
-        n_slots = splits_shared + splits_private
-        ws = ops.decode_fused_workspace(R, Hq, Hkv, D, n_slots, dev)
-        attn_out = torch.empty(R, Hq * D, device=dev, dtype=torch.bfloat16)
-        rope = ops.rope_table(max(plen) + C + 1, D, theta, dev)
-        h = torch.empty(R, d, device=dev, dtype=torch.bfloat16)
-        n_part = ((d + 127) // 128) * 4                                     # partial sum-of-squares rows a d-wide GEMM emits
-        ssq_a = torch.zeros(n_part, 32, device=dev, dtype=torch.float32)    # sum x^2 of the residual stream entering attention
-        ssq_b = torch.zeros(n_part, 32, device=dev, dtype=torch.float32)    # ... entering the MLP (see br_skinny_gemm_ex)
-        ssq_e = torch.zeros(1, 32, device=dev, dtype=torch.float32)         # ... of the embedding row (first layer)
-
-        samp_ws = ops.sample_workspace(R, cfg.vocab_size, dev)
+        cur0 = torch.tensor([plen[r // G] for r in range(R)], device=dev, dtype=torch.int32)
+        if not hit:
+            St.tokens = torch.full((R, C), pad_fill, device=dev, dtype=torch.int64)
+            St.next_ids = torch.zeros(R, device=dev, dtype=torch.int64)
+            St.finished = torch.zeros(R, device=dev, dtype=torch.int32)
+            St.step = torch.zeros(1, device=dev, dtype=torch.int32)
+            St.cur_len = cur0.clone()
+            St.uniforms = uniforms.clone() if params.do_sample else None
+            St.scratch = ops.skinny_scratch(max(cfg.vocab_size, 2 * cfg.intermediate_size), dev)
+            splits_shared = min(8, n_shared) if n_shared > 0 else 0
+            splits_private = 2 if n_shared > 0 else 8
+            cap = 3 * torch.cuda.get_device_properties(dev).multi_processor_count      # the fused kernel's merger items need co-residency
+            n_items = lambda ss, sp: (R // G) * Hkv * ss + R * Hkv * sp
+            while n_items(splits_shared, splits_private) > cap and (splits_shared > 1 or splits_private > 1):
+                if splits_private > 1 and (splits_private >= splits_shared or splits_shared <= 1):
+                    splits_private //= 2
+                else:
+                    splits_shared = max(1, splits_shared // 2)
+            if G * (Hq // Hkv) > 32:
+                raise NotImplementedError("fused decode attention handles G * Hq/Hkv <= 32 query vectors per kv head")
+            St.splits = (splits_shared, splits_private)
+            St.ws = ops.decode_fused_workspace(R, Hq, Hkv, D, splits_shared + splits_private, dev)
+            St.attn_out = torch.empty(R, Hq * D, device=dev, dtype=torch.bfloat16)
+            St.rope = ops.rope_table(max(plen) + C + 1, D, theta, dev)
+            St.h = torch.empty(R, d, device=dev, dtype=torch.bfloat16)
+            n_part_ = ((d + 127) // 128) * 4                                    # partial sum-of-squares rows a d-wide GEMM emits
+            St.ssq_a = torch.zeros(n_part_, 32, device=dev, dtype=torch.float32)    # sum x^2 of the residual stream entering attention
+            St.ssq_b = torch.zeros(n_part_, 32, device=dev, dtype=torch.float32)    # ... entering the MLP (see br_skinny_gemm_ex)
+            St.ssq_e = torch.zeros(1, 32, device=dev, dtype=torch.float32)          # ... of the embedding row (first layer)
+            St.samp_ws = ops.sample_workspace(R, cfg.vocab_size, dev)
+            St.graph = None
+        else:
+            St.tokens.fill_(pad_fill); St.finished.zero_(); St.step.zero_(); St.cur_len.copy_(cur0)
+            if params.do_sample:
+                St.uniforms.copy_(uniforms)
+        tokens, next_ids, finished, step, cur_len = St.tokens, St.next_ids, St.finished, St.step, St.cur_len
+        uniforms = St.uniforms
+        scratch, ws, attn_out, rope, h = St.scratch, St.ws, St.attn_out, St.rope, St.h
+        ssq_a, ssq_b, ssq_e, samp_ws = St.ssq_a, St.ssq_b, St.ssq_e, St.samp_ws
+        splits_shared, splits_private = St.splits
+        n_part = ((d + 127) // 128) * 4
 
         def sample(logits):
             ops.sample_next(logits, workspace=samp_ws, temperature=params.temperature, top_k=params.top_k, top_p=params.top_p, do_sample=params.do_sample,
@@ -226,10 +254,12 @@ class RolloutEngine:
         step += 1                                                         # cur_len stays: the first generated token sits at index plen
 
         F = cfg.intermediate_size
-        b_qkv = torch.empty(R, (Hq + 2 * Hkv) * D, device=dev, dtype=torch.bfloat16)
-        b_x2 = torch.empty(R, d, device=dev, dtype=torch.bfloat16)
-        b_act = torch.empty(R, F, device=dev, dtype=torch.bfloat16)
-        b_logits = torch.empty(R, cfg.vocab_size, device=dev, dtype=torch.float32)
+        if not hit:
+            St.b_qkv = torch.empty(R, (Hq + 2 * Hkv) * D, device=dev, dtype=torch.bfloat16)
+            St.b_x2 = torch.empty(R, d, device=dev, dtype=torch.bfloat16)
+            St.b_act = torch.empty(R, F, device=dev, dtype=torch.bfloat16)
+            St.b_logits = torch.empty(R, cfg.vocab_size, device=dev, dtype=torch.float32)
+        b_qkv, b_x2, b_act, b_logits = St.b_qkv, St.b_x2, St.b_act, St.b_logits
 
         use_chain = os.environ.get("BR_DECODE_CHAIN", "0") == "1"
 
@@ -271,25 +301,29 @@ class RolloutEngine:
         decode_step = decode_step_chain if use_chain else decode_step_5
 
         n_steps = C - 1
-        graph = None
-        if use_graph and n_steps > 2:
-            # warm up once on a side stream (allocator + lazy func attributes), then capture one decode step
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            state = [t.clone() for t in (tokens, next_ids, finished, step, cur_len)]
-            with torch.cuda.stream(s):
-                decode_step()
-            torch.cuda.current_stream().wait_stream(s)
-            for t, v in zip((tokens, next_ids, finished, step, cur_len), state):
-                t.copy_(v)                                                # the warm-up step is replayed for real below
-            graph = torch.cuda.CUDAGraph()
-            n0 = ops.LAUNCHES[0]
-            with torch.cuda.graph(graph):
-                decode_step()
-            per_replay = ops.LAUNCHES[0] - n0
-            ops.LAUNCHES[0] = n0
-            for t, v in zip((tokens, next_ids, finished, step, cur_len), state):
-                t.copy_(v)
+        if not hit:
+            St.decode_step = decode_step
+            St.per_replay = 0
+            if use_graph and n_steps > 2:
+                # warm up once on a side stream (allocator + lazy func attributes), then capture one decode step
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                state = [t.clone() for t in (tokens, next_ids, finished, step, cur_len)]
+                with torch.cuda.stream(s):
+                    decode_step()
+                torch.cuda.current_stream().wait_stream(s)
+                for t, v in zip((tokens, next_ids, finished, step, cur_len), state):
+                    t.copy_(v)                                                # the warm-up step is replayed for real below
+                St.graph = torch.cuda.CUDAGraph()
+                n0 = ops.LAUNCHES[0]
+                with torch.cuda.graph(St.graph):
+                    decode_step()
+                St.per_replay = ops.LAUNCHES[0] - n0
+                ops.LAUNCHES[0] = n0
+                for t, v in zip((tokens, next_ids, finished, step, cur_len), state):
+                    t.copy_(v)
+            self._cached[key] = St
+        graph, per_replay, decode_step = St.graph, St.per_replay, St.decode_step
         done_steps = 0
         check_every = 16
         while done_steps < n_steps:
@@ -303,7 +337,7 @@ class RolloutEngine:
             done_steps += chunk
             if eos >= 0 and done_steps < n_steps and bool(finished.min().item() == 1):
                 break
-        out = tokens
+        out = tokens.clone()                                                 # the static buffer is reused by the next rollout
         if eos >= 0:
             # HF stops as soon as every row has finished: trim to the longest row (eos position inclusive)
             is_eos = out == eos
