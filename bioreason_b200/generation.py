@@ -78,6 +78,35 @@ def group_size_from_flags(eq: List[bool]) -> int:
     return 1
 
 
+def plan_pages(plen: List[int], G: int, C: int):
+    """KV page plan of a rollout (host side, pure).  plen[u] = prompt length of unique prompt u; every prompt is sampled G times
+    for C new tokens.  Full prompt pages (the first n_shared of every group; one count for all groups) are shared by the G rows
+    of a group; the partially filled tail page and the pages of generated tokens are private per row.
+    Returns dict(n_shared, max_pages, n_pages, table [U*G][max_pages] (lists), prefill_pages [U] (pages holding the prompt,
+    i.e. row 0 of the group), tail_copies [(src_page, dst_page)] to replicate row 0's partially shared tail pages)."""
+    U = len(plen)
+    n_full = [l // PAGE for l in plen]
+    n_shared = min(n_full) if G > 1 else 0
+    priv = [math.ceil((l - n_shared * PAGE + C) / PAGE) for l in plen]
+    max_pages = n_shared + max(priv)
+    nxt = 0
+    table = [[0] * max_pages for _ in range(U * G)]
+    prefill_pages, tail_copies = [], []
+    for u in range(U):
+        shared = list(range(nxt, nxt + n_shared)); nxt += n_shared
+        for g in range(G):
+            r = u * G + g
+            mine = list(range(nxt, nxt + priv[u])); nxt += priv[u]
+            table[r][:n_shared] = shared
+            table[r][n_shared:n_shared + priv[u]] = mine
+        n_prompt_pages = math.ceil(plen[u] / PAGE)
+        prefill_pages.append(table[u * G][:n_prompt_pages])
+        for j in range(n_shared, n_prompt_pages):
+            for g in range(1, G):
+                tail_copies.append((table[u * G][j], table[u * G + g][j]))
+    return dict(n_shared=n_shared, max_pages=max_pages, n_pages=nxt, table=table, prefill_pages=prefill_pages, tail_copies=tail_copies)
+
+
 class RolloutEngine:
     """Owns the KV page pool, decode scratch and the captured decode-step graph for one model."""
 
@@ -137,23 +166,10 @@ class RolloutEngine:
         pos = engine.generate_positions(u_mask)
 
         # ---- page plan: full prompt pages are shared by the group, the tail page + generated tokens are private
-        n_full = [l // PAGE for l in plen]
-        n_shared = min(n_full) if G > 1 else 0                           # kernel takes one shared-page count for all groups
-        priv_pages = [math.ceil((l - n_shared * PAGE + C) / PAGE) for l in plen]
-        max_pages = n_shared + max(priv_pages)
-        next_page = 0
-        table = torch.zeros(B, max_pages, dtype=torch.int32)
-        prefill_pages = []                                               # per unique prompt: pages holding its prompt tokens (row 0 of the group)
-        for u in range(U):
-            shared = list(range(next_page, next_page + n_shared)); next_page += n_shared
-            for gidx in range(G):
-                r = u * G + gidx
-                mine = list(range(next_page, next_page + priv_pages[u])); next_page += priv_pages[u]
-                table[r, :n_shared] = torch.tensor(shared, dtype=torch.int32) if n_shared else table[r, :0]
-                table[r, n_shared:n_shared + priv_pages[u]] = torch.tensor(mine, dtype=torch.int32)
-            prefill_pages.append(table[u * G, :math.ceil(plen[u] / PAGE)].clone())
-        n_pages = next_page
-        table_host = table
+        plan = plan_pages(plen, G, C)
+        n_shared, max_pages, n_pages = plan["n_shared"], plan["max_pages"], plan["n_pages"]
+        table = torch.tensor(plan["table"], dtype=torch.int32)
+        prefill_pages = [torch.tensor(p, dtype=torch.int32) for p in plan["prefill_pages"]]
         nl = len(W.layers)
         # Static buffers + the captured decode graph are cached per rollout shape: a training run replays the same graph every
         # step (no per-step capture, no graph-pool / allocator churn -- that churn showed up as multi-second host stalls).
@@ -178,16 +194,10 @@ class RolloutEngine:
 
         hidden = engine.decoder_forward(W, emb, U, P, pos, ks, ke, kv_sink=kv_sink, lora=m._lora.w if m._lora is not None else None)
         # replicate each group's partially filled tail page to the other G-1 rows
-        if G > 1:
-            src, dst = [], []
-            for u in range(U):
-                n_tail = math.ceil(plen[u] / PAGE) - n_shared
-                for j in range(n_tail):
-                    for gidx in range(1, G):
-                        src.append(int(prefill_pages[u][n_shared + j])); dst.append(int(table_host[u * G + gidx, n_shared + j]))
-            if src:
-                s_t, d_t = torch.tensor(src, device=dev), torch.tensor(dst, device=dev)
-                kc[:, d_t] = kc[:, s_t]; vc[:, d_t] = vc[:, s_t]
+        if plan["tail_copies"]:
+            s_t = torch.tensor([a for a, _ in plan["tail_copies"]], device=dev)
+            d_t = torch.tensor([b for _, b in plan["tail_copies"]], device=dev)
+            kc[:, d_t] = kc[:, s_t]; vc[:, d_t] = vc[:, s_t]
 
         # ---- decode state
         R = B
