@@ -73,3 +73,36 @@ def test_forward_small_vs_oracle(B, n_seq, dna_len, text_len):
     mx, rmx, mean, rmean = _err_budget(logits, ref32, ref16, valid)
     print(f"small: max|err| {mx:.4g} (HF bf16: {rmx:.4g}); mean {mean:.4g} (HF bf16 {rmean:.4g}); logit std {ref32[valid].std():.3g}")
     assert mx <= 2.0 * rmx + 1e-3 and mean <= 2.0 * rmean + 1e-4
+
+
+@pytest.mark.skipif(__import__("os").environ.get("BR_SKIP_LARGE") == "1", reason="BR_SKIP_LARGE=1")
+def test_forward_config_a_real_shapes():
+    """BASELINE.json configs[0] / SURVEY.md §8d (a): NT-v2-500M + Qwen3-1.7B at the REAL widths and depths, one forward on
+    2 x 168-token DNA (1 002 bp) + 128-token prompt (L = 464), CUDA path vs the CPU oracle (HF fp32 and HF bf16)."""
+    import time
+    from bioreason_b200.configs import text_config, dna_config
+    from bioreason_b200.models import DNALLMModel
+    from oracle.models import build_oracle, synth_batch
+    torch.set_num_threads(min(32, __import__("os").cpu_count() or 8))
+    tc, dc = text_config("qwen3-1.7b"), dna_config("nt-v2-500m")
+    t0 = time.time()
+    oracle = build_oracle(tc, dc, seed=1234)
+    batch = synth_batch(tc, dc, batch=1, n_seq=2, dna_len=168, text_len=128, seed=1234)
+    assert batch["input_ids"].shape == (1, 128 + 2 * 168 + 4) or batch["input_ids"].shape[1] >= 464
+    with torch.no_grad():
+        ref32 = oracle(**batch).logits
+    t_cpu = time.time() - t0
+    m = DNALLMModel.from_oracle(oracle)
+    torch.cuda.synchronize(); t1 = time.time()
+    logits = m(**batch).logits.float().cpu()
+    t_gpu = time.time() - t1
+    with torch.no_grad():
+        ref16 = oracle.to(torch.bfloat16)(**batch).logits.float()
+    e_mine = (logits - ref32).abs(); e_ref = (ref16 - ref32).abs()
+    std = ref32.std().item()
+    print(f"config (a): L={batch['input_ids'].shape[1]} V={tc.vocab_size}; max|err| ours {e_mine.max():.4g} vs HF-bf16 {e_ref.max():.4g}; "
+          f"mean {e_mine.mean():.4g} vs {e_ref.mean():.4g}; logit std {std:.3g}; argmax agreement with fp32: ours "
+          f"{(logits.argmax(-1) == ref32.argmax(-1)).float().mean():.3f}, HF-bf16 {(ref16.argmax(-1) == ref32.argmax(-1)).float().mean():.3f}; "
+          f"oracle build+fwd {t_cpu:.0f}s, CUDA fwd (incl. lazy logits) {t_gpu * 1e3:.0f} ms")
+    assert e_mine.max().item() <= 2.0 * e_ref.max().item() + 1e-3
+    assert e_mine.mean().item() <= 2.0 * e_ref.mean().item() + 1e-4
