@@ -213,6 +213,22 @@ class DNALLMModel(nn.Module):
             aux = (enc, row_map)
         return (emb, aux) if return_proj_inputs else emb
 
+    def process_dna_embeddings(self, dna_tokenized: Dict[str, torch.Tensor], batch_idx_map: List[int], batch_size: int) -> List[torch.Tensor]:
+        """dna_llm.py:103-179 as a standalone call: encoder (no grad) -> projector -> the first `valid_length` rows of every
+        sequence, concatenated per batch item.  forward()/generate() do not go through this list form (the projector GEMM
+        scatters straight into the embedding buffer); it exists for callers that want the per-item DNA embeddings."""
+        dev = self._dec.embed.device
+        ids = dna_tokenized["input_ids"].to(dev)
+        mask = dna_tokenized["attention_mask"].to(dev)
+        with torch.no_grad():
+            enc = engine.encoder_forward(self._enc, ids, mask)                      # [n_seq * S, d_dna]
+        proj = ops.gemm(enc, self._proj_w16, bias=self._proj_b16).view(ids.shape[0], ids.shape[1], -1)
+        valid = mask.sum(dim=1).tolist()                                            # reference: one .item() per sequence (:168)
+        result = [[] for _ in range(batch_size)]
+        for seq_idx, batch_idx in enumerate(batch_idx_map):
+            result[batch_idx].append(proj[seq_idx, : valid[seq_idx]])
+        return [torch.cat(r, dim=0) if r else torch.zeros((0, self.text_hidden_size), device=dev, dtype=proj.dtype) for r in result]
+
     def forward(self, input_ids=None, attention_mask=None, dna_tokenized=None, batch_idx_map=None, labels=None, **kwargs):
         if input_ids is None or attention_mask is None:
             raise ValueError("Either 'inputs' or 'input_ids'/'attention_mask' must be provided")

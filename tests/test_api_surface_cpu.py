@@ -16,7 +16,7 @@ def _params(fn):
 
 def test_model_signatures_cover_reference():
     from bioreason_b200.models.dna_llm import DNALLMModel
-    for meth in ("__init__", "forward", "generate"):
+    for meth in ("__init__", "forward", "generate", "process_dna_embeddings"):
         ref = API["DNALLMModel"][meth]
         ours = _params(getattr(DNALLMModel, meth))
         for i, a in enumerate(ref["args"]):

@@ -40,6 +40,23 @@ def test_forward_tiny_golden(golden, tiny_oracle):
         m(input_ids=None, attention_mask=None)
 
 
+def test_process_dna_embeddings_tiny(golden, tiny_oracle):
+    """The list-returning public method (dna_llm.py:103-179): per batch item, the valid rows of its sequences, projected."""
+    from bioreason_b200.models import DNALLMModel
+    m = DNALLMModel.from_oracle(tiny_oracle)
+    b = golden["A"]["batch"]
+    B = b["input_ids"].shape[0]
+    with torch.no_grad():
+        want = tiny_oracle.process_dna_embeddings(b["dna_tokenized"], b["batch_idx_map"], B)
+    got = m.process_dna_embeddings(b["dna_tokenized"], b["batch_idx_map"], B)
+    assert len(got) == len(want) == B
+    for g, w in zip(got, want):
+        assert g.shape == w.shape
+        torch.testing.assert_close(g.float().cpu(), w, rtol=3e-2, atol=3e-2)
+    empty = m.process_dna_embeddings({k: v[:2] for k, v in b["dna_tokenized"].items()}, [1, 1], 3)
+    assert empty[0].shape[0] == 0 and empty[2].shape[0] == 0 and empty[1].shape[0] > 0
+
+
 def test_per_token_logps_tiny_golden(golden, tiny_oracle):
     from bioreason_b200.models import DNALLMModel
     m = DNALLMModel.from_oracle(tiny_oracle)
