@@ -158,6 +158,8 @@ def build_rollout_weights(dec_w, lora: "LoraState | None", out=None):
         ops.scale_columns_(out.lm_head, dec_w.final_norm)                  # frozen: folded once
     for i, (Lw, Lo) in enumerate(zip(dec_w.layers, out.layers)):
         if lora is not None:
+            if Lo.w_o.data_ptr() == Lw.w_o.data_ptr() or Lo.w_down.data_ptr() == Lw.w_down.data_ptr():
+                raise RuntimeError("rollout weights alias the frozen base weights (built before enable_lora); rebuild them with out=None")
             s, Ll, T = lora.scale, lora.w.layers[i], lora.wT[i]
             # [N, K] = B[N, r'] @ (A^T)[K, r']^T ; K-major operands: A_op = B (K = r'), B_op = A^T ([K, r'])
             ops.gemm(Ll.b_qkv, T["a_qkv_T"], alpha=s, residual=Lw.w_qkv, out=Lo.w_qkv)

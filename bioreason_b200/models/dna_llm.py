@@ -160,6 +160,11 @@ class DNALLMModel(nn.Module):
         does in reason.py:376-388, in kernel layout.  Freezes the base text model and the DNA encoder."""
         from ..lora import LoraState
         self._lora = LoraState(self.text_model, self._dec, r, alpha, seed)
+        # Rollout weights built before the adapters existed alias the frozen base w_o / w_down (nothing to merge then); a later
+        # merge into that object would write W + s*B*A INTO the base weights.  Drop them (and the decode graphs captured on them).
+        self._rollout_dec = None
+        if getattr(self, "_rollout", None) is not None:
+            self._rollout._cached.clear()
         for p in self.dna_model.parameters():
             p.requires_grad_(False)                                          # reason.py:371-372
         self._proj_ref = (self._proj_w16.clone(), self._proj_b16.clone())    # the reference policy's projector (deep copy at init)

@@ -63,6 +63,9 @@ class DNALLMGRPOConfig:
     bf16: bool = True
     gradient_checkpointing: bool = False
     eval_strategy: str = "no"
+    save_steps: int = 0                   # > 0: fire the callbacks' on_save every save_steps optimizer steps (HF save_strategy="steps")
+    save_safetensors: bool = False        # reason.py:597 sets it; saving itself is the callbacks' job (reason.py:46-81)
+    lora_dropout: float = 0.05            # accepted; the kernels apply no dropout (out of scope)
     # B200 build additions
     lora_r: int = 32
     lora_alpha: float = 64.0

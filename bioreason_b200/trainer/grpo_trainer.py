@@ -19,6 +19,7 @@ import torch.distributed as dist
 from torch.utils.data import Sampler
 
 from .. import dp, ops, training
+from . import rewards as rw
 from .grpo_config import DNALLMGRPOConfig
 
 
@@ -50,6 +51,41 @@ class RepeatRandomSampler(Sampler):
 
 def _world():
     return (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
+
+
+class TrainerState:
+    """The fields of transformers.TrainerState that callbacks on this path read (reason.py:46-81 uses global_step)."""
+
+    def __init__(self):
+        self.global_step, self.epoch, self.max_steps = 0, 0.0, 0
+        self.log_history: List[Dict[str, float]] = []
+        self.is_world_process_zero = _world()[0] == 0
+        self.is_local_process_zero = self.is_world_process_zero
+
+
+class TrainerControl:
+    def __init__(self):
+        self.should_save = self.should_log = self.should_training_stop = self.should_evaluate = self.should_epoch_stop = False
+
+
+class CallbackHandler:
+    """Duck-typed transformers.TrainerCallback dispatch: event(args, state, control, model=, processing_class=, optimizer=, ...);
+    a callback may return a (modified) control object."""
+
+    def __init__(self, callbacks, trainer):
+        self.callbacks, self.trainer = list(callbacks or []), trainer
+
+    def fire(self, event: str, **extra):
+        tr = self.trainer
+        for cb in self.callbacks:
+            fn = getattr(cb, event, None)
+            if fn is None:
+                continue
+            out = fn(tr.args, tr.state, tr.control, model=tr.model, processing_class=tr.processing_class, tokenizer=tr.processing_class,
+                     optimizer=tr.optimizer, train_dataloader=None, eval_dataloader=None, **extra)
+            if out is not None:
+                tr.control = out
+        return tr.control
 
 
 class DNALLMGRPOTrainer:
@@ -94,12 +130,26 @@ class DNALLMGRPOTrainer:
         self._metrics = defaultdict(list)
         self._buffered_inputs = [None] * a.gradient_accumulation_steps
         self._step = 0
-        self.global_step = 0
+        self.state, self.control = TrainerState(), TrainerControl()
+        self.state.max_steps = a.max_steps
+        self.callback_handler = CallbackHandler(callbacks, self)
+        self.reward_d2h_bytes = 0          # bytes of completion ids copied to the host for text reward functions (last step)
         # per-rank distinct sampling stream (set_seed(seed, device_specific=True), grpo_trainer.py:451)
         self._gen = torch.Generator(device="cuda")
         self._gen.manual_seed(a.seed + rank)
         self.timings = defaultdict(float)
         self._ev = []                      # (phase, start_event, end_event): GPU-side phase times, read by gpu_phase_ms()
+
+    @property
+    def global_step(self):
+        return self.state.global_step
+
+    @global_step.setter
+    def global_step(self, v):
+        self.state.global_step = v
+
+    def add_callback(self, cb):
+        self.callback_handler.callbacks.append(cb)
 
     def _mark(self, phase):
         """Context manager: CUDA-event bracket of a phase on the current stream (no host sync)."""
@@ -132,15 +182,22 @@ class DNALLMGRPOTrainer:
         return RepeatRandomSampler(self.train_dataset, self.num_generations, eff // self.num_generations, self.num_iterations, a.seed)
 
     def _prepare_prompt_inputs(self, inputs) -> Dict[str, Any]:
-        """Pre-tokenised batches pass through; raw examples go through dna_module + processor like :538-567."""
+        """Pre-tokenised batches pass through; raw examples go through dna_module + processor like :538-567.  Returns the model
+        inputs plus `_examples` (the raw example dicts, for the reward columns) and `_prompts`."""
         if isinstance(inputs, dict) and "input_ids" in inputs:
-            return inputs
+            out = dict(inputs)
+            out.setdefault("_examples", inputs.get("examples"))
+            out.setdefault("_prompts", inputs.get("prompts"))
+            return out
         if self.dna_module is None or self.processing_class is None:
             raise ValueError("raw examples need dna_module and processing_class (no tokenizer files exist offline); pass a tokenised batch")
         prompts_text = self.dna_module.prepare_prompt(self.processing_class, inputs)
         dnas = [x["dna_sequences"] for x in inputs]
-        return self.dna_module.prepare_model_inputs(self.processing_class, self.model, prompts_text, dnas, return_tensors="pt", padding=True,
-                                                    padding_side="left", add_special_tokens=False)
+        out = dict(self.dna_module.prepare_model_inputs(self.processing_class, self.model, prompts_text, dnas, return_tensors="pt", padding=True,
+                                                        padding_side="left", add_special_tokens=False))
+        out["_examples"] = list(inputs)
+        out["_prompts"] = [x["prompt"] for x in inputs]                                     # grpo_trainer.py:537
+        return out
 
     # ------------------------------------------------------------------ log-probs
     def _get_per_token_logps(self, model, input_ids, attention_mask, keep_last=None, lora="policy", **mm):
@@ -167,18 +224,25 @@ class DNALLMGRPOTrainer:
             completion_ids = model.generate(prompt_ids, prompt_mask, mm["dna_tokenized"], mm["batch_idx_map"], uniforms=uniforms, **self.generation_kwargs)
         self.timings["rollout"] += time.perf_counter() - t0
         completion_mask = ops.eos_mask(completion_ids, self.eos_token_id if not self.args.suppress_eos else -1)      # :605-609
+        # text reward functions need the ids on the host: start the copy now (side stream, pinned), wait for it only after the
+        # reference-policy forward has been queued -> decode + CPU rewards overlap that forward
+        need_text = rewards_per_func is None and any(not rw.wants_token_protocol(f) for f in self.reward_funcs)
+        host_copy = rw.AsyncHostCopy(completion_ids) if need_text else None
+        self.reward_d2h_bytes = host_copy.nbytes if host_copy is not None else 0
         ids = torch.cat([prompt_ids, completion_ids], dim=1)
         attention_mask = torch.cat([prompt_mask, completion_mask.to(prompt_mask.dtype)], dim=1)                       # :612
         Cc = completion_ids.shape[1]
         with self._mark("ref_logps"):
             old_lp = self._get_per_token_logps(model, ids, attention_mask, keep_last=Cc, **mm) if self.num_iterations > 1 else None
             ref_lp = self._get_per_token_logps(model, ids, attention_mask, keep_last=Cc, lora=None, **mm) if self.beta != 0.0 else None
-        # rewards: token-level callables f(completion_ids=, prompt_ids=, **batch) -> [B] floats (text rewards need a tokenizer)
+        # rewards: the reference protocol f(prompts=, completions=, **columns) on decoded text (:640-676); functions that name a
+        # `completion_ids` parameter get device tensors instead (trainer/rewards.py)
         if rewards_per_func is None:
-            rewards_per_func = torch.zeros(B, len(self.reward_funcs), device=dev)
-            for i, f in enumerate(self.reward_funcs):
-                out = f(completion_ids=completion_ids, prompt_ids=prompt_ids, completion_mask=completion_mask)
-                rewards_per_func[:, i] = torch.as_tensor(out, dtype=torch.float32, device=dev)
+            t_r = time.perf_counter()
+            rewards_per_func = rw.score(self.reward_funcs, examples=pi.get("_examples"), prompts=pi.get("_prompts"), completion_ids=completion_ids,
+                                        completion_mask=completion_mask, prompt_ids=prompt_ids, processing_class=self.processing_class,
+                                        host_copy=host_copy, extra_columns=pi.get("reward_kwargs"))
+            self.timings["reward_host"] += time.perf_counter() - t_r
         rewards_all = dp.gather_rewards(rewards_per_func)                                                              # C1, :679
         adv_all, gmean, gstd = ops.grpo_advantages(rewards_all, self.num_generations, return_stats=True)               # :682-692
         advantages = dp.local_slice(adv_all, B)                                                                        # :695-699
@@ -259,6 +323,17 @@ class DNALLMGRPOTrainer:
             model.sync_adapters(rollout=True)
         self.global_step += 1
         self.timings["optimizer"] += time.perf_counter() - t0
+        a = self.args
+        self.control = self.callback_handler.fire("on_step_end")
+        if getattr(a, "logging_steps", 0) and self.callback_handler.callbacks and self.global_step % max(1, int(a.logging_steps)) == 0:
+            logs = self.log_metrics()
+            self.state.log_history.append(dict(logs, step=self.global_step))
+            self.control = self.callback_handler.fire("on_log", logs=logs)
+        if getattr(a, "save_steps", 0) and self.global_step % int(a.save_steps) == 0:
+            self.control.should_save = True
+        if self.control.should_save:
+            self.control = self.callback_handler.fire("on_save")               # reason.py:46-81 SaveWithPyTorchCallback hooks here
+            self.control.should_save = False
 
     def train(self, batches=None, max_steps: Optional[int] = None):
         """Iterate tokenised batches (or the dataset through RepeatRandomSampler) for max_steps optimizer steps."""
@@ -268,10 +343,13 @@ class DNALLMGRPOTrainer:
             sampler = list(iter(self._get_train_sampler()))
             batches = ([self.train_dataset[i] for i in idx] for idx in dp.rank_batches(sampler, a.per_device_train_batch_size))
         out = []
+        self.control = self.callback_handler.fire("on_train_begin")
         for b in batches:
+            self.control = self.callback_handler.fire("on_step_begin")
             out.append(self.training_step(b))
-            if steps is not None and self.global_step >= steps:
+            if (steps is not None and self.global_step >= steps) or self.control.should_training_stop:
                 break
+        self.control = self.callback_handler.fire("on_train_end")
         return out
 
     def log_metrics(self) -> Dict[str, float]:

@@ -68,3 +68,27 @@ def test_synth_generators_agree():
     y = b(tc, dc, batch=3, n_seq=2, dna_len=[9, 7, 9], text_len=[20, 14, 11], seed=5)
     assert torch.equal(x["input_ids"], y["input_ids"]) and torch.equal(x["dna_tokenized"]["input_ids"], y["dna_tokenized"]["input_ids"])
     assert x["batch_idx_map"] == y["batch_idx_map"]
+
+
+def test_generate_before_enable_lora_keeps_base_weights_frozen():
+    """rollout weights built before the adapters exist alias the frozen base w_o / w_down; the per-step merge must
+    never write into them (zero-shot eval -> trainer construction -> optimizer steps)."""
+    from bioreason_b200.configs import text_config, dna_config
+    from bioreason_b200.models import DNALLMModel
+    from bioreason_b200.trainer import DNALLMGRPOConfig, DNALLMGRPOTrainer
+    from oracle.models import build_oracle, synth_batch
+    tc, dc = text_config("tiny"), dna_config("tiny")
+    m = DNALLMModel.from_oracle(build_oracle(tc, dc, seed=5))
+    batch = synth_batch(tc, dc, batch=4, n_seq=2, dna_len=10, text_len=18, seed=3, same_prompt=True)
+    m.generate(batch["input_ids"], batch["attention_mask"], batch["dna_tokenized"], batch["batch_idx_map"], max_new_tokens=4, do_sample=False)
+    assert m._rollout_dec is not None
+    base = [(L.w_o.clone(), L.w_down.clone(), L.w_qkv.clone(), L.w_gu.clone()) for L in m._dec.layers]
+    cfg = DNALLMGRPOConfig(num_generations=4, max_completion_length=4, per_device_train_batch_size=4, learning_rate=5e-2, lora_r=16, lora_alpha=32.0)
+    tr = DNALLMGRPOTrainer(m, [_token_reward], cfg)                       # enable_lora + sync_adapters(rollout=True) inside
+    for _ in range(2):
+        tr.training_step(batch)
+    for L, (wo, wd, wq, wg) in zip(m._dec.layers, base):
+        assert torch.equal(L.w_o, wo) and torch.equal(L.w_down, wd) and torch.equal(L.w_qkv, wq) and torch.equal(L.w_gu, wg)
+    for L, Lr in zip(m._dec.layers, m._rollout_dec.layers):
+        assert Lr.w_o.data_ptr() != L.w_o.data_ptr() and Lr.w_down.data_ptr() != L.w_down.data_ptr()
+        assert not torch.equal(Lr.w_o, L.w_o)                             # adapters moved -> merged weights differ from the base

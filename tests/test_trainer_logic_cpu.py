@@ -15,6 +15,8 @@ def _fake_trainer(beta, mu, micro_rows, ga=1):
     t = object.__new__(DNALLMGRPOTrainer)
     t.args = types.SimpleNamespace(micro_rows=micro_rows, gradient_accumulation_steps=ga)
     t.beta, t.num_iterations, t.epsilon_low, t.epsilon_high = beta, mu, 0.2, 0.2
+    from bioreason_b200.trainer.grpo_trainer import TrainerState
+    t.state = TrainerState()
     t.global_step, t._step = 0, 0
     t._buffered_inputs = [None] * ga
     t._metrics = collections.defaultdict(list)
