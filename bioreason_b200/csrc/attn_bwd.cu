@@ -231,6 +231,11 @@ __global__ void dq_convert_kernel(const float* __restrict__ acc, bf16* __restric
 
 }  // namespace
 
+int br_attn_bwd_tc5_impl(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o, int64_t ldo,
+                         const void* dout, int64_t lddo, const float* lse, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                         int B, int L, int n_q_heads, int n_kv_heads, const int32_t* kv_start, const int32_t* kv_end, float scale,
+                         void* workspace, cudaStream_t st);
+
 extern "C" {
 
 int64_t br_attn_bwd_workspace_bytes(int B, int L, int n_q_heads, int head_dim) {
@@ -244,6 +249,10 @@ int br_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
     BR_CHECK_ARG(B > 0 && L > 0 && n_q_heads % n_kv_heads == 0, "attn_bwd: bad shape");
     constexpr int D = 128;
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool legacy = getenv("BR_ATTN_LEGACY") != nullptr;       // debugging switch: the previous mma.sync kernel
+    if (!legacy)
+        return br_attn_bwd_tc5_impl(q, ldq, k, ldk, v, ldv, o, ldo, dout, lddo, lse, dq, lddq, dk, lddk, dv, lddv, B, L, n_q_heads, n_kv_heads,
+                                    kv_start, kv_end, scale, workspace, st);
     BwdParams p;
     p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v; p.o = (const bf16*)o; p.dout = (const bf16*)dout;
     p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo; p.lddo = lddo; p.lse = lse;

@@ -1,0 +1,445 @@
+// Flash attention backward on tcgen05 / TMEM / TMA (sm_100a; causal GQA decoder rows, head_dim 128) -- autograd counterpart of
+// attn_fwd_tc5.cu.  Probabilities are recomputed from Q, K and the saved log-sum-exp; no score matrix, no
+// fp32 atomics and no dQ workspace ever touch HBM, and every output element is produced by exactly one CTA in a fixed order, so
+// the gradients are bit-reproducible run to run.
+//
+// Two kernels (7 tile GEMMs per (query tile, key tile) pair instead of the 5 of an atomics-based single pass; all on tcgen05):
+//   dq kernel   : CTA = 128-query tile of one (row, query head); loops over the key tiles it can see.
+//                   S  = Q K^T              (SS: both operands K-major in shared memory)
+//                   dP = dO V^T             (SS)
+//                   dS = P o (dP - delta) * scale   by 128 threads (thread <-> query row == TMEM lane), bf16 into TMEM over dP
+//                   dQ += dS K              (TS: A = dS in TENSOR MEMORY, B = the K tile as it landed, MN-major descriptor)
+//                 also computes delta = rowsum(dO o O) for its rows and publishes it for the dk/dv kernel.
+//   dk/dv kernel: CTA = 128-key tile of one (row, kv head); loops over the query heads of the group and the query tiles that
+//                 can see the keys; dK and dV accumulate in TMEM for the whole loop.
+//                   S^T  = K Q^T,  dP^T = V dO^T                 (SS)
+//                   P^T, dS^T (thread <-> key row) bf16 into TMEM over S^T / dP^T
+//                   dV += P^T dO,  dK += dS^T Q                  (TS; dO and Q tiles are MN-major B operands)
+// TMEM: 384 / 512 columns; one CTA per SM (192 KB of shared memory: two resident tiles + a 2-stage ring of two streamed tiles).
+#include "br_common.cuh"
+#include "../../include/bioreason_b200.h"
+
+namespace {
+
+constexpr int D = 128, BT = 128, NTHREADS = 192;
+constexpr int BLK = 128 * 128;            // bytes of a [128 rows x 64 cols] swizzled block
+constexpr int TILE = 2 * BLK;             // a 128 x 128 bf16 tile
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct BwdParams {
+    const bf16 *o, *dout; long long ldo, lddo;
+    const float* lse;        // [B, Hq, L]
+    float* delta;            // [B, Hq, L]  (written by the dq kernel, read by the dk/dv kernel)
+    bf16 *dq, *dk, *dv; long long lddq, lddk, lddv;
+    int B, L, Hq, Hkv;
+    const int *kv_start, *kv_end;
+    float scale, scale_log2;
+};
+
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// SS GEMM of two K-major 128 x 128 tiles: acc[128 x 128] = A . B^T
+__device__ __forceinline__ void mma_ss_kmajor(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr) {
+    constexpr uint32_t idesc = br::make_idesc_bf16(128, 128);
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) {
+        const uint32_t off = (kk >> 2) * BLK + (kk & 3) * 32;
+        br::tc_mma_bf16(tmem_d, br::make_sw128_kmajor_desc(a_addr + off), br::make_sw128_kmajor_desc(b_addr + off), idesc, kk != 0);
+    }
+}
+// TS GEMM: acc[128 x 128] (+)= A(tmem, 128 x 128 bf16 packed in 64 columns) . B, B = a [128 (K) x 128 (N)] row-major tile (MN-major)
+__device__ __forceinline__ void mma_ts_mnmajor(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_addr, bool accumulate) {
+    constexpr uint32_t idesc = br::make_idesc_bf16_major(128, 128, 0, 1);
+#pragma unroll
+    for (int kk = 0; kk < BT / 16; ++kk)
+        br::tc_mma_bf16_ts(tmem_d, tmem_a + kk * 8, br::make_sw128_mnmajor_desc(b_addr + kk * 2048, BLK, 1024), idesc, accumulate || kk != 0);
+}
+__device__ __forceinline__ void tma_tile(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int col0, int row0) {
+    br::tma_load_2d(dst, tm, bar, col0, row0);
+    br::tma_load_2d(dst + BLK, tm, bar, col0 + 64, row0);
+}
+__device__ __forceinline__ void store_row_bf16(bf16* dst, const uint32_t (&r)[32], float mul) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint4 w;
+        w.x = br::pack_bf16(__uint_as_float(r[q * 8 + 0]) * mul, __uint_as_float(r[q * 8 + 1]) * mul);
+        w.y = br::pack_bf16(__uint_as_float(r[q * 8 + 2]) * mul, __uint_as_float(r[q * 8 + 3]) * mul);
+        w.z = br::pack_bf16(__uint_as_float(r[q * 8 + 4]) * mul, __uint_as_float(r[q * 8 + 5]) * mul);
+        w.w = br::pack_bf16(__uint_as_float(r[q * 8 + 6]) * mul, __uint_as_float(r[q * 8 + 7]) * mul);
+        *reinterpret_cast<uint4*>(dst + q * 8) = w;
+    }
+}
+
+// =====================================================================================================================
+// dq kernel
+// =====================================================================================================================
+constexpr int DQ_OFF_Q = 0, DQ_OFF_DO = TILE, DQ_OFF_K = 2 * TILE, DQ_OFF_V = 4 * TILE, DQ_OFF_BAR = 6 * TILE;
+constexpr int DQ_SMEM = DQ_OFF_BAR + 256 + 1024;
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const __grid_constant__ CUtensorMap tmDO, const BwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_OFF_BAR);
+    uint64_t* qdo_full = bars;            // 1
+    uint64_t* k_full = bars + 1;          // 2
+    uint64_t* v_full = bars + 3;          // 2
+    uint64_t* k_empty = bars + 5;         // 2
+    uint64_t* v_empty = bars + 7;         // 2
+    uint64_t* sdp_full = bars + 9;        // S and dP of the current tile ready
+    uint64_t* ds_full = bars + 10;        // dS in TMEM
+    uint64_t* dq_final = bars + 11;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qb = gridDim.x - 1 - blockIdx.x;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int hk = h / (p.Hq / p.Hkv);
+    const int q0 = qb * BT;
+    const int ks = p.kv_start ? p.kv_start[b] : 0;
+    const int ke = p.kv_end ? p.kv_end[b] : p.L;
+    const int last_key = min(ke - 1, q0 + BT - 1);
+    const int jb_lo = ks / BT;
+    int jb_hi = last_key >= 0 ? last_key / BT : -1;
+    if (ke <= ks) jb_hi = jb_lo - 1;
+    const int n_tiles = max(0, jb_hi - jb_lo + 1);
+
+    if (warp == 0 && lane == 0) {
+        br::tma_prefetch_desc(&tmQ); br::tma_prefetch_desc(&tmK); br::tma_prefetch_desc(&tmV); br::tma_prefetch_desc(&tmDO);
+        br::mbar_init(qdo_full, 1);
+        for (int s = 0; s < 2; ++s) { br::mbar_init(&k_full[s], 1); br::mbar_init(&v_full[s], 1); br::mbar_init(&k_empty[s], 1); br::mbar_init(&v_empty[s], 1); }
+        br::mbar_init(sdp_full, 1); br::mbar_init(ds_full, 4); br::mbar_init(dq_final, 1);
+        br::mbar_fence_init();
+    }
+    if (warp == 1) { br::tmem_alloc(tmem_slot, 512); br::tmem_relinquish(); }
+    br::tc_fence_before();
+    __syncthreads();
+    br::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 128, tm_dq = tmem_base + 256;
+
+    if (warp == 0) {
+        if (lane == 0 && n_tiles > 0) {
+            const int row_q = b * p.L + q0;
+            br::mbar_expect_tx(qdo_full, 2 * TILE);
+            tma_tile(smem + DQ_OFF_Q, &tmQ, qdo_full, h * D, row_q);
+            tma_tile(smem + DQ_OFF_DO, &tmDO, qdo_full, h * D, row_q);
+            for (int t = 0; t < n_tiles; ++t) {
+                const int s = t & 1; const uint32_t ph = (t >> 1) & 1;
+                const int row_k = b * p.L + (jb_lo + t) * BT;
+                br::mbar_wait(&k_empty[s], ph ^ 1);
+                br::mbar_expect_tx(&k_full[s], TILE);
+                tma_tile(smem + DQ_OFF_K + s * TILE, &tmK, &k_full[s], hk * D, row_k);
+                br::mbar_wait(&v_empty[s], ph ^ 1);
+                br::mbar_expect_tx(&v_full[s], TILE);
+                tma_tile(smem + DQ_OFF_V + s * TILE, &tmV, &v_full[s], hk * D, row_k);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && n_tiles > 0) {
+            const uint32_t q_addr = br::smem_u32(smem + DQ_OFF_Q), do_addr = br::smem_u32(smem + DQ_OFF_DO);
+            br::mbar_wait(qdo_full, 0);
+            br::tc_fence_after();
+            for (int t = 0; t < n_tiles; ++t) {
+                const int s = t & 1; const uint32_t ph = (t >> 1) & 1;
+                const uint32_t k_addr = br::smem_u32(smem + DQ_OFF_K + s * TILE), v_addr = br::smem_u32(smem + DQ_OFF_V + s * TILE);
+                br::mbar_wait(&k_full[s], ph);
+                br::tc_fence_after();
+                mma_ss_kmajor(tm_s, q_addr, k_addr);                       // S = Q K^T
+                br::mbar_wait(&v_full[s], ph);
+                br::tc_fence_after();
+                mma_ss_kmajor(tm_dp, do_addr, v_addr);                     // dP = dO V^T
+                br::tc_commit(sdp_full);
+                br::tc_commit(&v_empty[s]);
+                br::mbar_wait(ds_full, t & 1);
+                br::tc_fence_after();
+                mma_ts_mnmajor(tm_dq, tm_dp, k_addr, t != 0);              // dQ += dS K
+                br::tc_commit(&k_empty[s]);
+            }
+            br::tc_commit(dq_final);
+        }
+    } else {
+        const int lane_grp = warp & 3;
+        const int row = lane_grp * 32 + lane;
+        const int i_glob = q0 + row;
+        const bool row_ok = i_glob < p.L;
+        const uint32_t lane_off = (uint32_t)(lane_grp * 32) << 16;
+        const long long tok = (long long)b * p.L + i_glob;
+        // ---- delta = rowsum(dO o O) for this query row (fp32), published for the dk/dv kernel
+        float delta = 0.f;
+        if (row_ok) {
+            const uint4* op = reinterpret_cast<const uint4*>(p.o + tok * p.ldo + (long long)h * D);
+            const uint4* dp = reinterpret_cast<const uint4*>(p.dout + tok * p.lddo + (long long)h * D);
+#pragma unroll 4
+            for (int c = 0; c < D / 8; ++c) {
+                const uint4 a = __ldg(op + c), g = __ldg(dp + c);
+                const float2 a0 = br::unpack_bf16(a.x), a1 = br::unpack_bf16(a.y), a2 = br::unpack_bf16(a.z), a3 = br::unpack_bf16(a.w);
+                const float2 g0 = br::unpack_bf16(g.x), g1 = br::unpack_bf16(g.y), g2 = br::unpack_bf16(g.z), g3 = br::unpack_bf16(g.w);
+                delta += a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y + a3.x * g3.x + a3.y * g3.y;
+            }
+            p.delta[((long long)b * p.Hq + h) * p.L + i_glob] = delta;
+        }
+        const float lse2 = row_ok ? p.lse[((long long)b * p.Hq + h) * p.L + i_glob] * LOG2E : INFINITY;
+        const float delta_s = delta * p.scale;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int k0 = (jb_lo + t) * BT;
+            const bool need_mask = (k0 < ks) || (k0 + BT > ke) || (k0 + BT - 1 > q0);
+            br::mbar_wait(sdp_full, t & 1);
+            br::tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BT; c += 32) {
+                uint32_t rs[32], rp[32];
+                br::tmem_ld_32x32(tm_s + lane_off + c, rs);
+                br::tmem_ld_32x32(tm_dp + lane_off + c, rp);
+                br::tmem_ld_wait();
+                uint32_t pk[16];
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    float x0 = __uint_as_float(rs[e]) * p.scale_log2 - lse2, x1 = __uint_as_float(rs[e + 1]) * p.scale_log2 - lse2;
+                    if (need_mask) {
+                        const int j = k0 + c + e;
+                        x0 = ((j >= ks) && (j < ke) && (j <= i_glob)) ? x0 : -INFINITY;
+                        x1 = ((j + 1 >= ks) && (j + 1 < ke) && (j + 1 <= i_glob)) ? x1 : -INFINITY;
+                    }
+                    const float p0 = ex2(x0), p1 = ex2(x1);
+                    const float d0 = p0 * fmaf(__uint_as_float(rp[e]), p.scale, -delta_s), d1 = p1 * fmaf(__uint_as_float(rp[e + 1]), p.scale, -delta_s);
+                    pk[e >> 1] = br::pack_bf16(d0, d1);
+                }
+                br::tmem_st_32x16(tm_dp + lane_off + (c >> 1), pk);       // dS over the consumed dP columns
+            }
+            br::tmem_st_wait();
+            br::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) br::mbar_arrive(ds_full);
+        }
+        bf16* dq_row = p.dq + tok * p.lddq + (long long)h * D;
+        if (n_tiles > 0) {
+            br::mbar_wait(dq_final, 0);
+            br::tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < D; c += 32) {
+                uint32_t r[32];
+                br::tmem_ld_32x32(tm_dq + lane_off + c, r);
+                br::tmem_ld_wait();
+                if (row_ok) store_row_bf16(dq_row + c, r, 1.f);
+            }
+        } else if (row_ok) {
+#pragma unroll
+            for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dq_row + c) = make_uint4(0, 0, 0, 0);
+        }
+    }
+    br::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { br::tc_fence_after(); br::tmem_dealloc(tmem_base, 512); }
+}
+
+// =====================================================================================================================
+// dk / dv kernel
+// =====================================================================================================================
+constexpr int KV_OFF_K = 0, KV_OFF_V = TILE, KV_OFF_Q = 2 * TILE, KV_OFF_DO = 4 * TILE, KV_OFF_VEC = 6 * TILE, KV_OFF_BAR = KV_OFF_VEC + 2 * 2 * 128 * 4;
+constexpr int KV_SMEM = KV_OFF_BAR + 256 + 1024;
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                    const __grid_constant__ CUtensorMap tmDO, const BwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* s_vec = reinterpret_cast<float*>(smem + KV_OFF_VEC);           // [stage][0: lse*log2e, 1: delta*scale][128 queries]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + KV_OFF_BAR);
+    uint64_t* kv_full = bars;             // 1
+    uint64_t* q_full = bars + 1;          // 2
+    uint64_t* do_full = bars + 3;         // 2
+    uint64_t* qdo_empty = bars + 5;       // 2
+    uint64_t* sdp_full = bars + 7;
+    uint64_t* pds_full = bars + 8;
+    uint64_t* acc_final = bars + 9;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int jb = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+    const int GQ = p.Hq / p.Hkv;
+    const int key0 = jb * BT;
+    const int ks = p.kv_start ? p.kv_start[b] : 0;
+    const int ke = p.kv_end ? p.kv_end[b] : p.L;
+    const bool block_live = (key0 < ke) && (key0 + BT > ks) && (key0 < p.L);
+    const int n_ib = (p.L + BT - 1) / BT;
+    const int per_head = n_ib - jb;                                       // causal: query tiles jb .. n_ib-1 see these keys
+    const int iters = block_live ? GQ * per_head : 0;
+
+    if (warp == 0 && lane == 0) {
+        br::tma_prefetch_desc(&tmQ); br::tma_prefetch_desc(&tmK); br::tma_prefetch_desc(&tmV); br::tma_prefetch_desc(&tmDO);
+        br::mbar_init(kv_full, 1);
+        for (int s = 0; s < 2; ++s) { br::mbar_init(&q_full[s], 1); br::mbar_init(&do_full[s], 1); br::mbar_init(&qdo_empty[s], 1); }
+        br::mbar_init(sdp_full, 1); br::mbar_init(pds_full, 4); br::mbar_init(acc_final, 1);
+        br::mbar_fence_init();
+    }
+    if (warp == 1) { br::tmem_alloc(tmem_slot, 512); br::tmem_relinquish(); }
+    br::tc_fence_before();
+    __syncthreads();
+    br::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 128, tm_dv = tmem_base + 256, tm_dk = tmem_base + 384;
+
+    if (warp == 0) {
+        if (lane == 0 && iters > 0) {
+            const int row_k = b * p.L + key0;
+            br::mbar_expect_tx(kv_full, 2 * TILE);
+            tma_tile(smem + KV_OFF_K, &tmK, kv_full, hk * D, row_k);
+            tma_tile(smem + KV_OFF_V, &tmV, kv_full, hk * D, row_k);
+            for (int it = 0; it < iters; ++it) {
+                const int s = it & 1; const uint32_t ph = (it >> 1) & 1;
+                const int h = hk * GQ + it / per_head, ib = jb + it % per_head;
+                const int row_q = b * p.L + ib * BT;
+                br::mbar_wait(&qdo_empty[s], ph ^ 1);
+                br::mbar_expect_tx(&q_full[s], TILE);
+                tma_tile(smem + KV_OFF_Q + s * TILE, &tmQ, &q_full[s], h * D, row_q);
+                br::mbar_expect_tx(&do_full[s], TILE);
+                tma_tile(smem + KV_OFF_DO + s * TILE, &tmDO, &do_full[s], h * D, row_q);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && iters > 0) {
+            const uint32_t k_addr = br::smem_u32(smem + KV_OFF_K), v_addr = br::smem_u32(smem + KV_OFF_V);
+            br::mbar_wait(kv_full, 0);
+            br::tc_fence_after();
+            for (int it = 0; it < iters; ++it) {
+                const int s = it & 1; const uint32_t ph = (it >> 1) & 1;
+                const uint32_t q_addr = br::smem_u32(smem + KV_OFF_Q + s * TILE), do_addr = br::smem_u32(smem + KV_OFF_DO + s * TILE);
+                br::mbar_wait(&q_full[s], ph);
+                br::tc_fence_after();
+                mma_ss_kmajor(tm_s, k_addr, q_addr);                       // S^T = K Q^T
+                br::mbar_wait(&do_full[s], ph);
+                br::tc_fence_after();
+                mma_ss_kmajor(tm_dp, v_addr, do_addr);                     // dP^T = V dO^T
+                br::tc_commit(sdp_full);
+                br::mbar_wait(pds_full, it & 1);
+                br::tc_fence_after();
+                mma_ts_mnmajor(tm_dv, tm_s, do_addr, it != 0);             // dV += P^T dO
+                mma_ts_mnmajor(tm_dk, tm_dp, q_addr, it != 0);             // dK += dS^T Q
+                br::tc_commit(&qdo_empty[s]);
+            }
+            br::tc_commit(acc_final);
+        }
+    } else {
+        const int lane_grp = warp & 3;
+        const int row = lane_grp * 32 + lane;                              // key row inside the tile == TMEM lane
+        const int et = threadIdx.x - 64;                                   // 0..127
+        const int j_glob = key0 + row;
+        const bool key_ok = (j_glob >= ks) && (j_glob < ke);
+        const uint32_t lane_off = (uint32_t)(lane_grp * 32) << 16;
+        // per-query vectors of the next iteration, one element per thread, fetched one iteration ahead
+        auto fetch_vec = [&](int it, float& l2, float& ds) {
+            const int h = hk * GQ + it / per_head, ib = jb + it % per_head;
+            const int i = ib * BT + et;
+            l2 = INFINITY; ds = 0.f;
+            if (it < iters && i < p.L) {
+                const long long off = ((long long)b * p.Hq + h) * p.L + i;
+                l2 = __ldg(p.lse + off) * LOG2E; ds = __ldg(p.delta + off) * p.scale;
+            }
+        };
+        float nl2, nds;
+        fetch_vec(0, nl2, nds);
+        for (int it = 0; it < iters; ++it) {
+            const int s = it & 1;
+            const int ib = jb + it % per_head;
+            const int q0 = ib * BT;
+            float* v_l2 = s_vec + s * 256; float* v_ds = v_l2 + 128;
+            v_l2[et] = nl2; v_ds[et] = nds;
+            fetch_vec(it + 1, nl2, nds);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const bool need_mask = (ib == jb) || (key0 < ks) || (key0 + BT > ke) || (q0 + BT > p.L);
+            br::mbar_wait(sdp_full, it & 1);
+            br::tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BT; c += 32) {
+                uint32_t rs[32], rp[32];
+                br::tmem_ld_32x32(tm_s + lane_off + c, rs);
+                br::tmem_ld_32x32(tm_dp + lane_off + c, rp);
+                br::tmem_ld_wait();
+                uint32_t pk[16], dk_[16];
+#pragma unroll
+                for (int e = 0; e < 32; e += 4) {
+                    const float4 l4 = *reinterpret_cast<const float4*>(v_l2 + c + e), d4 = *reinterpret_cast<const float4*>(v_ds + c + e);
+                    const float ll[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
+                    float pr[4], dsv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float x = __uint_as_float(rs[e + u]) * p.scale_log2 - ll[u];
+                        if (need_mask) { const int i = q0 + c + e + u; x = (key_ok && j_glob <= i) ? x : -INFINITY; }   // i >= L rows carry lse = +inf
+                        pr[u] = ex2(x);
+                        dsv[u] = pr[u] * fmaf(__uint_as_float(rp[e + u]), p.scale, -dd[u]);
+                    }
+                    pk[e >> 1] = br::pack_bf16(pr[0], pr[1]); pk[(e >> 1) + 1] = br::pack_bf16(pr[2], pr[3]);
+                    dk_[e >> 1] = br::pack_bf16(dsv[0], dsv[1]); dk_[(e >> 1) + 1] = br::pack_bf16(dsv[2], dsv[3]);
+                }
+                br::tmem_st_32x16(tm_s + lane_off + (c >> 1), pk);        // P^T over the consumed S^T columns
+                br::tmem_st_32x16(tm_dp + lane_off + (c >> 1), dk_);      // dS^T over the consumed dP^T columns
+            }
+            br::tmem_st_wait();
+            br::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) br::mbar_arrive(pds_full);
+        }
+        const bool row_ok = j_glob < p.L;
+        const long long tok = (long long)b * p.L + j_glob;
+        bf16* dk_row = p.dk + tok * p.lddk + (long long)hk * D;
+        bf16* dv_row = p.dv + tok * p.lddv + (long long)hk * D;
+        if (iters > 0) {
+            br::mbar_wait(acc_final, 0);
+            br::tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < D; c += 32) {
+                uint32_t r[32];
+                br::tmem_ld_32x32(tm_dv + lane_off + c, r);
+                br::tmem_ld_wait();
+                if (row_ok) store_row_bf16(dv_row + c, r, 1.f);
+                br::tmem_ld_32x32(tm_dk + lane_off + c, r);
+                br::tmem_ld_wait();
+                if (row_ok) store_row_bf16(dk_row + c, r, 1.f);
+            }
+        } else if (row_ok) {
+#pragma unroll
+            for (int c = 0; c < D; c += 8) { *reinterpret_cast<uint4*>(dk_row + c) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(dv_row + c) = make_uint4(0, 0, 0, 0); }
+        }
+    }
+    br::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { br::tc_fence_after(); br::tmem_dealloc(tmem_base, 512); }
+}
+
+}  // namespace
+
+int br_attn_bwd_tc5_impl(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o, int64_t ldo,
+                         const void* dout, int64_t lddo, const float* lse, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                         int B, int L, int n_q_heads, int n_kv_heads, const int32_t* kv_start, const int32_t* kv_end, float scale,
+                         void* workspace, cudaStream_t st) {
+    BwdParams p;
+    p.o = (const bf16*)o; p.dout = (const bf16*)dout; p.ldo = ldo; p.lddo = lddo; p.lse = lse; p.delta = (float*)workspace;
+    p.dq = (bf16*)dq; p.dk = (bf16*)dk; p.dv = (bf16*)dv; p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
+    p.B = B; p.L = L; p.Hq = n_q_heads; p.Hkv = n_kv_heads; p.kv_start = kv_start; p.kv_end = kv_end;
+    p.scale = scale; p.scale_log2 = scale * LOG2E;
+    BR_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0,
+                 "attn_bwd: strides must be multiples of 8 elements");
+    BR_CHECK_ARG(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o | (uintptr_t)dout | (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) % 16 == 0,
+                 "attn_bwd: tensors must be 16-byte aligned");
+    CUtensorMap tq, tk, tv, tdo;
+    int rc;
+    const uint64_t rows = (uint64_t)B * L;
+    if ((rc = br_make_tmap_2d_bf16(&tq, q, rows, (uint64_t)n_q_heads * D, ldq, BT))) return rc;
+    if ((rc = br_make_tmap_2d_bf16(&tk, k, rows, (uint64_t)n_kv_heads * D, ldk, BT))) return rc;
+    if ((rc = br_make_tmap_2d_bf16(&tv, v, rows, (uint64_t)n_kv_heads * D, ldv, BT))) return rc;
+    if ((rc = br_make_tmap_2d_bf16(&tdo, dout, rows, (uint64_t)n_q_heads * D, lddo, BT))) return rc;
+    static bool done = false;
+    if (!done) {
+        BR_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+        BR_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KV_SMEM));
+        done = true;
+    }
+    const int nb = (L + BT - 1) / BT;
+    attn_bwd_dq_kernel<<<dim3(nb, n_q_heads, B), NTHREADS, DQ_SMEM, st>>>(tq, tk, tv, tdo, p);
+    BR_CHECK_LAUNCH();
+    attn_bwd_dkv_kernel<<<dim3(nb, n_kv_heads, B), NTHREADS, KV_SMEM, st>>>(tq, tk, tv, tdo, p);
+    BR_CHECK_LAUNCH();
+    return BR_OK;
+}

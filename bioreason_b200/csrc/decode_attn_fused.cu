@@ -76,6 +76,24 @@ __device__ __forceinline__ void norm_rope_words(uint32_t wlo, uint32_t whi, cons
     }
 }
 
+// same arithmetic with the norm weights and the (cos, sin) pairs already in registers
+template <int D>
+__device__ __forceinline__ void norm_rope_words_pre(uint32_t wlo, uint32_t whi, const float (&wl)[D / 64], const float (&wh)[D / 64],
+                                                    const float2 (&cs_sn)[D / 64], float eps, float (&olo)[D / 64], float (&ohi)[D / 64]) {
+    constexpr int E = D / 64;
+    const float2 a2 = br::unpack_bf16(wlo), b2 = br::unpack_bf16(whi);
+    const float lo[E] = {a2.x, a2.y}, hi[E] = {b2.x, b2.y};
+    const float ss = a2.x * a2.x + a2.y * a2.y + b2.x * b2.x + b2.y * b2.y;
+    const float rstd = rsqrtf(br::warp_sum(ss) / (float)D + eps);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const float a = rbf(wl[e] * rbf(lo[e] * rstd)), b = rbf(wh[e] * rbf(hi[e] * rstd));
+        const float cs = cs_sn[e].x, sn = cs_sn[e].y;
+        olo[e] = rbf(a * cs) + rbf(-b * sn);
+        ohi[e] = rbf(b * cs) + rbf(a * sn);
+    }
+}
+
 // Quarter-warp version: 8 lanes own one 128-wide head vector (lane `sub` holds dims [8 sub, 8 sub + 8) of each half), so a warp
 // ropes 4 query vectors at once.  in/out: lo[8], hi[8] fp32.
 template <int D>
@@ -151,8 +169,11 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     STAMP(0);
     br::launch_dependents();
-    br::grid_dep_wait();
-    STAMP(1);
+    // ------------------------------------------------------------------------------------------------------------------
+    // Everything up to grid_dep_wait() depends only on state the PREVIOUS kernel of the chain (this step's qkv GEMM) does not
+    // touch: page table, cur_len, rope table, norm weights and the KV pages of earlier tokens.  It is issued before the wait,
+    // so the KV fetch (DRAM latency, queued behind the weight stream) overlaps the qkv GEMM instead of following it.
+    // ------------------------------------------------------------------------------------------------------------------
     const int n_groups = p.R / p.G;
     const int n_shared_items = (p.n_shared_pages > 0 && p.SS > 0) ? n_groups * p.Hkv * p.SS : 0;
     int item = blockIdx.x;
@@ -173,40 +194,74 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
     int kv_len = 0, pg_lo, pg_hi;
     if (shared_pass) { pg_lo = split; pg_hi = n_sh; }
     else { kv_len = __ldcg(p.cur_len + row_base) + 1; pg_lo = n_sh + split; pg_hi = (kv_len + 63) >> 6; }
+    // the page that receives this step's token (private pass): its tile may only be loaded after the append below
+    const int newest_pg = shared_pass ? -1 : ((kv_len - 1) >> 6);
+    const bool owns_newest = !shared_pass && newest_pg >= pg_lo && (newest_pg - pg_lo) % n_splits == 0;
+
+    auto tile_src = [&](const bf16* cache, int pg) { return cache + (long long)table[pg] * page_stride + (long long)kvh * 64 * D; };
+    auto issue_tile = [&](int st, int pg) {
+        load_tile<D, NT>(sK + st * TILE, tile_src(p.kcache, pg), D, 0, 64, tid);
+        load_tile<D, NT>(sV + st * TILE, tile_src(p.vcache, pg), D, 0, 64, tid);
+    };
+    const int pg1 = pg_lo + n_splits;
+    const bool have0 = pg_lo < pg_hi, have1 = pg1 < pg_hi;
+    const bool early0 = have0 && pg_lo != newest_pg, early1 = have1 && pg1 != newest_pg;
+    if (early0) issue_tile(0, pg_lo);
+    if (early1) issue_tile(1, pg1);
+    cp_async_commit();
+
+    // query-prep operands that do not depend on the new tokens: positions, norm weights, rope pairs
+    const int q4 = lane >> 3, sub = lane & 7;
+    int posv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int s = warp * 16 + i * 4 + q4;
+        const int rr = s / p.GQ;
+        const bool ok = rr < rows_per_unit && (row_base + rr) < p.R;
+        posv[i] = ok ? __ldcg(p.cur_len + row_base + rr) : -1;
+    }
+    float wl[8], wh[8];
+    { uint4 a = __ldg(reinterpret_cast<const uint4*>(p.qw + sub * 8)), b = __ldg(reinterpret_cast<const uint4*>(p.qw + 64 + sub * 8)); unpack8(a, wl); unpack8(b, wh); }
+    bool table_ok = p.rope != nullptr;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) table_ok &= (posv[i] < p.rope_n_pos);
+    table_ok = __all_sync(0xffffffffu, table_ok);               // warp-uniform: the shuffles below use the full mask
+    float2 tcs[4][8];
+    if (table_ok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4* tp = reinterpret_cast<const float4*>(p.rope + (long long)(posv[i] < 0 ? 0 : posv[i]) * (D / 2) + sub * 8);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const float4 t4 = __ldg(tp + e); tcs[i][2 * e] = make_float2(t4.x, t4.y); tcs[i][2 * e + 1] = make_float2(t4.z, t4.w); }
+        }
+    }
+    // new-token K: norm weight + rope pair of the lane's two dims (owner item, warp 0)
+    float2 kcs[E]; float kwl[E], kwh[E];
+    const bool k_table = owns_newest && p.rope != nullptr && (kv_len - 1) < p.rope_n_pos;
+    if (owns_newest && warp == 0) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int j = lane * E + e;
+            kwl[e] = __bfloat162float(p.kw[j]); kwh[e] = __bfloat162float(p.kw[D / 2 + j]);
+            kcs[e] = k_table ? __ldg(p.rope + (long long)(kv_len - 1) * (D / 2) + j) : make_float2(0.f, 0.f);
+        }
+    }
+    br::grid_dep_wait();
+    STAMP(1);
 
     // ---- queries: norm + rope straight into the swizzled smem tile (slot s -> row s / GQ, head kvh*GQ + s % GQ)
     {
         // 8 lanes per query vector, 4 vectors per warp per pass, 4 passes: all 16-byte L2 loads are issued before any is used
-        const int q4 = lane >> 3, sub = lane & 7;
-        uint4 rl[4], rh[4]; int posv[4];
+        uint4 rl[4], rh[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int s = warp * 16 + i * 4 + q4;
             const int rr = s / p.GQ, hh = kvh * p.GQ + s % p.GQ;
-            const bool ok = rr < rows_per_unit && (row_base + rr) < p.R;
-            rl[i] = rh[i] = make_uint4(0, 0, 0, 0); posv[i] = -1;
-            if (ok) {
-                const int row = row_base + rr;
-                const bf16* src = p.qkv + (long long)row * p.ld + (long long)hh * D;
+            rl[i] = rh[i] = make_uint4(0, 0, 0, 0);
+            if (posv[i] >= 0) {
+                const bf16* src = p.qkv + (long long)(row_base + rr) * p.ld + (long long)hh * D;
                 rl[i] = __ldcg(reinterpret_cast<const uint4*>(src + sub * 8));
                 rh[i] = __ldcg(reinterpret_cast<const uint4*>(src + 64 + sub * 8));
-                posv[i] = __ldcg(p.cur_len + row);
-            }
-        }
-        // norm weights and (when the table covers every position) the cos/sin pairs of all 4 passes are fetched up front too
-        float wl[8], wh[8];
-        { uint4 a = __ldg(reinterpret_cast<const uint4*>(p.qw + sub * 8)), b = __ldg(reinterpret_cast<const uint4*>(p.qw + 64 + sub * 8)); unpack8(a, wl); unpack8(b, wh); }
-        bool table_ok = p.rope != nullptr;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) table_ok &= (posv[i] < p.rope_n_pos);
-        table_ok = __all_sync(0xffffffffu, table_ok);               // warp-uniform: the shuffles below use the full mask
-        float2 tcs[4][8];
-        if (table_ok) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4* tp = reinterpret_cast<const float4*>(p.rope + (long long)(posv[i] < 0 ? 0 : posv[i]) * (D / 2) + sub * 8);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { const float4 t4 = __ldg(tp + e); tcs[i][2 * e] = make_float2(t4.x, t4.y); tcs[i][2 * e + 1] = make_float2(t4.z, t4.w); }
             }
         }
         STAMP(8);
@@ -227,36 +282,31 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
     }
     STAMP(9);
     // ---- append the new token's K / V (private item that owns the newest page)
-    if (!shared_pass) {
+    if (owns_newest) {
         const int pos = kv_len - 1;
-        const int last_pg = pos >> 6;
-        if (last_pg >= pg_lo && (last_pg - pg_lo) % n_splits == 0) {
-            const int page = table[last_pg], slot = pos & 63;
-            if (warp == 0) {
-                float olo[E], ohi[E];
-                uint32_t kwlo, kwhi;
-                load_head_words(p.qkv + (long long)row_base * p.ld + (long long)(p.Hq + kvh) * D, lane, kwlo, kwhi);
-                norm_rope_words<D>(kwlo, kwhi, p.kw, pos, p.theta, p.eps, lane, olo, ohi, p.rope, p.rope_n_pos);
-                bf16* dst = p.kcache + ((long long)page * p.Hkv + kvh) * 64 * D + (long long)slot * D;
-                const int j0 = lane * E;
-                *reinterpret_cast<uint32_t*>(dst + j0) = br::pack_bf16(olo[0], olo[1]);
-                *reinterpret_cast<uint32_t*>(dst + D / 2 + j0) = br::pack_bf16(ohi[0], ohi[1]);
-            } else {
-                const bf16* src = p.qkv + (long long)row_base * p.ld + (long long)(p.Hq + p.Hkv + kvh) * D;
-                bf16* dst = p.vcache + ((long long)page * p.Hkv + kvh) * 64 * D + (long long)slot * D;
-                if (lane < D / 8) reinterpret_cast<uint4*>(dst)[lane] = __ldcg(reinterpret_cast<const uint4*>(src) + lane);
-            }
-            __threadfence();
+        const int page = table[newest_pg], slot = pos & 63;
+        if (warp == 0) {
+            float olo[E], ohi[E];
+            uint32_t kwlo, kwhi;
+            load_head_words(p.qkv + (long long)row_base * p.ld + (long long)(p.Hq + kvh) * D, lane, kwlo, kwhi);
+            if (k_table) norm_rope_words_pre<D>(kwlo, kwhi, kwl, kwh, kcs, p.eps, olo, ohi);
+            else norm_rope_words<D>(kwlo, kwhi, p.kw, pos, p.theta, p.eps, lane, olo, ohi, p.rope, p.rope_n_pos);
+            bf16* dst = p.kcache + ((long long)page * p.Hkv + kvh) * 64 * D + (long long)slot * D;
+            const int j0 = lane * E;
+            *reinterpret_cast<uint32_t*>(dst + j0) = br::pack_bf16(olo[0], olo[1]);
+            *reinterpret_cast<uint32_t*>(dst + D / 2 + j0) = br::pack_bf16(ohi[0], ohi[1]);
+        } else {
+            const bf16* src = p.qkv + (long long)row_base * p.ld + (long long)(p.Hq + p.Hkv + kvh) * D;
+            bf16* dst = p.vcache + ((long long)page * p.Hkv + kvh) * 64 * D + (long long)slot * D;
+            if (lane < D / 8) reinterpret_cast<uint4*>(dst)[lane] = __ldcg(reinterpret_cast<const uint4*>(src) + lane);
         }
+        __threadfence();
     }
     __syncthreads();
     STAMP(2);
-
-    auto tile_src = [&](const bf16* cache, int pg) { return cache + (long long)table[pg] * page_stride + (long long)kvh * 64 * D; };
-    if (pg_lo < pg_hi) {
-        load_tile<D, NT>(sK, tile_src(p.kcache, pg_lo), D, 0, 64, tid);
-        load_tile<D, NT>(sV, tile_src(p.vcache, pg_lo), D, 0, 64, tid);
-    }
+    // the newest page, if it is one of the first two tiles of this item, could not be fetched before the append
+    if (have0 && !early0) issue_tile(0, pg_lo);
+    if (have1 && !early1) issue_tile(1, pg1);
     cp_async_commit();
 
     uint32_t qf[D / 16][4];
@@ -278,10 +328,7 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
         const int st = it & 1;
         uint8_t* cK = sK + st * TILE;
         uint8_t* cV = sV + st * TILE;
-        if (pg + n_splits < pg_hi) {
-            load_tile<D, NT>(sK + (st ^ 1) * TILE, tile_src(p.kcache, pg + n_splits), D, 0, 64, tid);
-            load_tile<D, NT>(sV + (st ^ 1) * TILE, tile_src(p.vcache, pg + n_splits), D, 0, 64, tid);
-        }
+        if (it >= 1 && pg + n_splits < pg_hi) issue_tile(st ^ 1, pg + n_splits);      // tiles 0 and 1 were issued before the loop
         cp_async_commit();
         if (warp_live) {
             float s[BN / 8][4];

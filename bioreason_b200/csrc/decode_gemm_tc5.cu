@@ -4,12 +4,15 @@
 // built around bytes in flight, not FLOPs:
 //   * swap-AB: the weight matrix is the M operand (128 output features per UMMA, M=128), the R live rows of X are the N operand
 //     (N = 16 or 32; TMA zero-fills the rows beyond R), accumulator [128 features x N] fp32 in TMEM;
-//   * one persistent CTA per SM; a TMA producer warp keeps a 10-stage ring of 128x64 weight tiles (16 KB each, 128B-swizzled)
-//     in flight -- ~180 KB of outstanding HBM reads per SM independent of occupancy -- an MMA warp issues tcgen05.mma,
-//     4 epilogue warps drain TMEM;
+//   * one persistent CTA per SM; a TMA producer warp keeps a 6-stage ring of 128x64 weight tiles (16 KB each, 128B-swizzled)
+//     in flight (108 KB of shared memory, so this kernel and its PDL successor co-reside on an SM; the successor fills its ring
+//     BEFORE it waits for this kernel -- weights are constant during a rollout); an MMA warp issues tcgen05.mma, 4 epilogue
+//     warps drain TMEM.  (Pulling more of the chunk into L2 ahead of time was measured SLOWER: more bytes in flight only add
+//     queueing delay to the small latency-critical messages -- partial tiles, counters, activations.);
 //   * stream-K: the (feature tile, k block) units of the whole layer are cut into equal contiguous chunks, one per CTA, so
 //     small-N layers (o_proj / down_proj: 20 feature tiles) still load all 148 SMs evenly.  A tile finished by several CTAs
-//     is reduced with fp32 atomics into a scratch tile; the last arriver applies the epilogue and re-zeros the scratch.
+//     is reduced deterministically: every contributor writes its fp32 partial tile to its own scratch slot, the last arriver
+//     (arrival counter) sums the slots in ascending CTA order and applies the epilogue -- no floating-point atomics.
 // Epilogues: bf16 store, +residual, SwiGLU over (8 gate | 8 up) feature blocks, fp32 logits.
 // PDL: the kernel is launched with programmatic stream serialization.  Kernels chained this way are NOT separated by the
 // usual launch-boundary L1 invalidation, so every load of data another kernel of the chain rewrites (residual, statistics,
@@ -33,6 +36,9 @@ struct SkParams {
     // columns); sumsq_out[(tile*4 + warp), r] = sum over that warp's 32 features of out[r, f]^2 (bf16-rounded) -- partials are
     // written, never accumulated with atomics, and summed in a fixed order by the consumer: the rollout is reproducible.
     const float* sumsq_in; int sumsq_in_n; float* sumsq_out; float eps;
+    long long* dbg; int dbg_slot;       // optional %globaltimer stamps [slot][cta][8] (profiling aid)
+    int w_evict_first;                  // weight tiles are read once per token step: mark them evict-first in L2 so the small
+                                        // latency-critical buffers (activations, partial tiles, statistics, tables) stay resident
 };
 
 __device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16(x)); }
@@ -56,9 +62,21 @@ struct SL {
     static constexpr int TOTAL = TILE_BYTES + 1024 + 1024;   // + barriers / flags / per-row rstd + alignment slack
 };
 
+// residual values of feature f for all live rows, issued as independent L2 loads (one round trip instead of R dependent ones);
+// called BEFORE the accumulator wait so the latency hides under the weight stream
+template <int BNX>
+__device__ __forceinline__ void load_residual(const SkParams& p, int f, float (&res)[BNX]) {
+    const bool on = p.mode == 1 && f < p.N;
+#pragma unroll
+    for (int r = 0; r < BNX; ++r) {
+        res[r] = 0.f;
+        if (on && r < p.R) res[r] = __bfloat162float(__ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(p.res) + (long long)r * p.ldr + f)));
+    }
+}
+
 // per-feature epilogue: v[r] = sum for row r of feature f
 template <int BNX>
-__device__ __forceinline__ void apply_epilogue(const SkParams& p, int f, int lane, const float (&v)[BNX], const float* s_rs, int part_row) {
+__device__ __forceinline__ void apply_epilogue(const SkParams& p, int f, int lane, const float (&v)[BNX], const float (&res)[BNX], const float* s_rs, int part_row) {
     const bool f_ok = f < p.N;
     float rs[BNX];
 #pragma unroll
@@ -76,23 +94,27 @@ __device__ __forceinline__ void apply_epilogue(const SkParams& p, int f, int lan
         }
         return;
     }
+    float sq[BNX];
 #pragma unroll
     for (int r = 0; r < BNX; ++r) {
-        if (r >= p.R) break;                                   // warp-uniform
-        float x = v[r] * rs[r];
-        float sq = 0.f;
-        if (f_ok) {
+        sq[r] = 0.f;
+        if (r < p.R && f_ok) {
+            float x = v[r] * rs[r];
             if (p.mode == 3) reinterpret_cast<float*>(p.out)[(long long)r * p.ldo + f] = x;
             else {
-                if (p.mode == 1) x = rbf(x) + __bfloat162float(__ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(p.res) + (long long)r * p.ldr + f)));
+                if (p.mode == 1) x = rbf(x) + res[r];
                 const bf16 xb = __float2bfloat16(x);
                 reinterpret_cast<bf16*>(p.out)[(long long)r * p.ldo + f] = xb;
-                sq = __bfloat162float(xb) * __bfloat162float(xb);
+                sq[r] = __bfloat162float(xb) * __bfloat162float(xb);
             }
         }
-        if (p.sumsq_out) {
-            sq = br::warp_sum(sq);
-            if (lane == 0) p.sumsq_out[(long long)part_row * 32 + r] = sq;
+    }
+    if (p.sumsq_out) {
+#pragma unroll
+        for (int r = 0; r < BNX; ++r) {
+            if (r >= p.R) break;                                   // warp-uniform
+            const float t = br::warp_sum(sq[r]);
+            if (lane == 0) p.sumsq_out[(long long)part_row * 32 + r] = t;
         }
     }
 }
@@ -107,12 +129,12 @@ __device__ __forceinline__ void compute_row_rstd(const SkParams& p, int et, floa
     if (p.sumsq_in && r < p.R) {
         const int n = p.sumsq_in_n;
         const int per = (n + 3) >> 2, lo = q * per, hi = min(n, lo + per);
-        for (int i = lo; i < hi; i += 8) {
-            float t[8];
+        for (int i = lo; i < hi; i += 32) {                       // 32 independent L2 loads in flight: one round trip for d <= 4096
+            float t[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) t[j] = (i + j < hi) ? __ldcg(p.sumsq_in + (long long)(i + j) * 32 + r) : 0.f;
+            for (int j = 0; j < 32; ++j) t[j] = (i + j < hi) ? __ldcg(p.sumsq_in + (long long)(i + j) * 32 + r) : 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc += t[j];
+            for (int j = 0; j < 32; ++j) acc += t[j];               // fixed order: reproducible
         }
     }
     s_part[q * 32 + r] = acc;
@@ -124,6 +146,9 @@ __device__ __forceinline__ void compute_row_rstd(const SkParams& p, int et, floa
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
 }
+
+__device__ __forceinline__ long long gtime_sk() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define SKSTAMP(k) do { if (p.dbg && (threadIdx.x == 64)) p.dbg[((long long)p.dbg_slot * 160 + blockIdx.x) * 8 + (k)] = gtime_sk(); } while (0)
 
 template <int BNX>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -165,10 +190,15 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             // The weights are constant during the rollout: fill the whole ring with weight tiles BEFORE waiting for the
             // previous kernel (PDL), so the HBM stream of this layer overlaps the tail of the previous kernel.
             const int n_pre = min(L::NSTAGE, u_hi - u_lo);
+            const uint64_t pol = br::make_policy_evict_first();
+            auto load_w = [&](void* dst, uint64_t* bar, int c0, int c1) {
+                if (p.w_evict_first) br::tma_load_2d_hint(dst, &tmW, bar, c0, c1, pol);
+                else br::tma_load_2d(dst, &tmW, bar, c0, c1);
+            };
             for (int i = 0; i < n_pre; ++i) {
                 const int u = u_lo + i, tile = u / p.KB, kb = u - tile * p.KB;
                 br::mbar_expect_tx(&full_bar[i], L::STAGE);
-                br::tma_load_2d(smem + i * L::STAGE, &tmW, &full_bar[i], kb * BK, tile * BM);
+                load_w(smem + i * L::STAGE, &full_bar[i], kb * BK, tile * BM);
             }
             br::grid_dep_wait();
             for (int i = 0; i < n_pre; ++i) {
@@ -181,7 +211,7 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 br::mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* sa = smem + s * L::STAGE;
                 br::mbar_expect_tx(&full_bar[s], L::STAGE);
-                br::tma_load_2d(sa, &tmW, &full_bar[s], kb * BK, tile * BM);
+                load_w(sa, &full_bar[s], kb * BK, tile * BM);
                 br::tma_load_2d(sa + L::A_BYTES, &tmX, &full_bar[s], kb * BK, 0);
                 if (++s == L::NSTAGE) { s = 0; ph ^= 1; }
             }
@@ -215,15 +245,23 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     } else {
         const int lane_grp = warp & 3;
         const int et = threadIdx.x - 64;                      // 0..127 within the epilogue group
+        SKSTAMP(0);
         br::grid_dep_wait();                                  // everything below touches data shared with earlier kernels
+        SKSTAMP(1);
         compute_row_rstd(p, et, s_rs, s_rs + 32);
+        SKSTAMP(2);
         int as = 0; uint32_t aph = 0;
         int u = u_lo;
         while (u < u_hi) {
             const int tile = u / p.KB;
             const int seg_end = min(u_hi, (tile + 1) * p.KB);
             const bool whole = (u == tile * p.KB) && (seg_end == (tile + 1) * p.KB);
+            const int f = tile * BM + lane_grp * 32 + lane;
+            const int part_row = tile * 4 + lane_grp;
+            float res[BNX];
+            load_residual<BNX>(p, f, res);                        // in flight while the accumulator is still being produced
             br::mbar_wait(&tfull_bar[as], aph);
+            if (u == u_lo) SKSTAMP(3);
             br::tc_fence_after();
             const uint32_t taddr = tmem_base + as * BNX + ((uint32_t)(lane_grp * 32) << 16);
             float v[BNX];
@@ -240,49 +278,58 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             __syncwarp();
             if (lane == 0) br::mbar_arrive(&tempty_bar[as]);   // accumulator drained into registers
             if (++as == 2) { as = 0; aph ^= 1; }
-            const int f = tile * BM + lane_grp * 32 + lane;
-            const int part_row = tile * 4 + lane_grp;
             if (whole) {
-                apply_epilogue<BNX>(p, f, lane, v, s_rs, part_row);
+                apply_epilogue<BNX>(p, f, lane, v, res, s_rs, part_row);
             } else {
-                // deterministic stream-K: write this CTA's partial tile to its own scratch slot; the last arriver adds the
-                // partials of the contributing CTAs in ascending CTA order (no floating-point atomics anywhere)
+                // Deterministic stream-K exchange.  A tile that spans several CTAs is finished by the FIRST of them (lowest index):
+                // for that CTA the tile is the last segment of its chunk, so it has nothing else left to do, while every other
+                // contributor meets the tile at the START of its chunk and publishes early.  Contributors store their fp32 partial
+                // tile to their scratch slot and signal with one release-reduction per warp (no CTA barrier, no fence, no returning
+                // atomic); the reducer acquires the counter, gathers all partials in ONE batch of independent L2 loads and adds them
+                // to its own registers in ascending CTA order -- no floating-point atomics, bit-reproducible.
                 const int first_c = (tile * p.KB) / p.chunk, last_c = ((tile + 1) * p.KB - 1) / p.chunk;
-                const int my_slot = (tile == u_lo / p.KB) ? 0 : 1;
-                float* mine = p.scratch + (((long long)blockIdx.x * 2 + my_slot) * BNX) * BM + lane_grp * 32 + lane;
+                if ((int)blockIdx.x != first_c) {
+                    float* mine = p.scratch + ((long long)blockIdx.x * 2 * BNX) * BM + lane_grp * 32 + lane;   // slot 0: the CTA's first tile
 #pragma unroll
-                for (int r = 0; r < BNX; ++r)
-                    if (r < p.R) __stcg(mine + r * BM, v[r]);
-                __threadfence();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (et == 0) *s_flag = (atomicAdd(p.counters + tile, 1) == last_c - first_c);
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (*s_flag) {
-                    __threadfence();
-#pragma unroll
-                    for (int r = 0; r < BNX; ++r) v[r] = 0.f;
-                    for (int c0 = first_c; c0 <= last_c; c0 += 4) {             // 4 contributors' loads in flight at a time
-                        float t[4][BNX];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int c = c0 + j;
-                            const int slot = (tile == (c * p.chunk) / p.KB) ? 0 : 1;
-                            const float* src = p.scratch + (((long long)c * 2 + slot) * BNX) * BM + lane_grp * 32 + lane;
-#pragma unroll
-                            for (int r = 0; r < BNX; ++r) t[j][r] = (c <= last_c && r < p.R) ? __ldcg(src + r * BM) : 0.f;
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-#pragma unroll
-                            for (int r = 0; r < BNX; ++r) v[r] += t[j][r];                  // ascending CTA order: deterministic
+                    for (int r = 0; r < BNX; ++r)
+                        if (r < p.R) __stcg(mine + r * BM, v[r]);
+                    __syncwarp();
+                    if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.counters + tile) : "memory");
+                    if (seg_end == u_hi) SKSTAMP(4);
+                } else {
+                    if (et == 0) {
+                        const unsigned want = 4u * (unsigned)(last_c - first_c);
+                        unsigned seen;
+                        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.counters + tile) : "memory"); } while (seen < want);
+                        p.counters[tile] = 0;                                    // nobody touches it again before the next launch
                     }
-                    if (et == 0) p.counters[tile] = 0;
-                    apply_epilogue<BNX>(p, f, lane, v, s_rs, part_row);
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    SKSTAMP(4);
+                    for (int c0 = first_c + 1; c0 <= last_c; c0 += 8) {          // 8 contributors x 8 rows of loads in flight
+#pragma unroll
+                        for (int r0 = 0; r0 < BNX; r0 += 8) {
+                            if (r0 >= p.R) break;                                // warp-uniform
+                            float t[8][8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float* src = p.scratch + ((long long)(c0 + j) * 2 * BNX) * BM + lane_grp * 32 + lane;
+#pragma unroll
+                                for (int r = 0; r < 8; ++r) t[j][r] = (c0 + j <= last_c && r0 + r < p.R) ? __ldcg(src + (r0 + r) * BM) : 0.f;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                                for (int r = 0; r < 8; ++r) v[r0 + r] += t[j][r];            // ascending CTA order: deterministic
+                        }
+                    }
+                    SKSTAMP(5);
+                    apply_epilogue<BNX>(p, f, lane, v, res, s_rs, part_row);
+                    SKSTAMP(6);
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");     // s_flag reusable
             }
             u = seg_end;
         }
+        SKSTAMP(7);
     }
     br::tc_fence_before();
     __syncthreads();
@@ -453,8 +500,10 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) skinny_chain_kernel(const __
                 if (++as == 2) { as = 0; aph ^= 1; }
                 const int f = tile * BM + lane_grp * 32 + lane;
                 const int part_row = tile * 4 + lane_grp;
+                float res[BNX];
+                load_residual<BNX>(p, f, res);
                 if (whole) {
-                    apply_epilogue<BNX>(p, f, lane, v, s_rs, part_row);
+                    apply_epilogue<BNX>(p, f, lane, v, res, s_rs, part_row);
                 } else {
                     const int first_c = (tile * p.KB) / p.chunk, last_c = ((tile + 1) * p.KB - 1) / p.chunk;
                     const int my_slot = (tile == u_lo / p.KB) ? 0 : 1;
@@ -486,7 +535,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) skinny_chain_kernel(const __
                                 for (int r = 0; r < BNX; ++r) v[r] += t[j][r];
                         }
                         if (et == 0) p.counters[tile] = 0;
-                        apply_epilogue<BNX>(p, f, lane, v, s_rs, part_row);
+                        apply_epilogue<BNX>(p, f, lane, v, res, s_rs, part_row);
                     }
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
@@ -534,6 +583,9 @@ int launch_chain(const ChainParams& cp, int grid, cudaStream_t st) {
 
 }  // namespace
 
+static long long* g_sk_dbg = nullptr;
+static int g_sk_dbg_slot = 0;
+
 extern "C" {
 
 int64_t br_skinny_scratch_bytes(int max_N) {
@@ -562,6 +614,8 @@ int br_skinny_gemm_ex(const void* X, int64_t ldx, const void* W, int64_t ldw, vo
     p.scratch = (float*)scratch; p.counters = (int*)((float*)scratch + (int64_t)br_num_sms() * 2 * 32 * BM) + 16;
     p.sumsq_in = sumsq_in; p.sumsq_in_n = sumsq_in_n; p.sumsq_out = sumsq_out; p.eps = eps;
     BR_CHECK_ARG(!(sumsq_out && mode >= 2), "skinny_gemm: sumsq_out only with bf16 outputs (mode 0/1)");
+    p.dbg = g_sk_dbg; p.dbg_slot = g_sk_dbg ? g_sk_dbg_slot++ : 0;
+    { const char* e = getenv("BR_SKINNY_EVICT_FIRST"); p.w_evict_first = e ? atoi(e) : 1; }
     p.tiles_n = (N + BM - 1) / BM; p.KB = (K + BK - 1) / BK; p.units = p.tiles_n * p.KB;
     int grid = p.units < br_num_sms() ? p.units : br_num_sms();
     p.chunk = (p.units + grid - 1) / grid;
@@ -575,6 +629,11 @@ int br_skinny_gemm_ex(const void* X, int64_t ldx, const void* W, int64_t ldw, vo
     return BNX == 16 ? launch<16>(tw, tx, p, grid, st) : launch<32>(tw, tx, p, grid, st);
 }
 
+
+/* profiling aid: [n_launches, 160, 8] int64 %globaltimer stamps of the next br_skinny_gemm launches (NULL disables):
+ * 0 start, 1 dependency wait passed, 2 row statistics ready, 3 first accumulator, 4 last partial published, 5 reduction loads done,
+ * 6 reducer epilogue done, 7 CTA done */
+int br_skinny_debug(long long* buf) { g_sk_dbg = buf; g_sk_dbg_slot = 0; return BR_OK; }
 
 static long long* g_chain_dbg = nullptr;
 /* profiling aid: [n_sms, 32] int64 %globaltimer stamps of the next chain launches (NULL disables) */
@@ -597,7 +656,7 @@ int br_skinny_chain(const br_skinny_phase* phases, int n_phases, int R, float ep
         SkParams& p = cp.ph[i].p;
         p.R = R; p.N = h.N; p.K = h.K; p.mode = h.mode; p.out = h.out; p.ldo = h.ldo; p.res = (const bf16*)h.residual; p.ldr = h.ldr;
         p.scratch = part; p.counters = cp.gbar + 16;
-        p.sumsq_in = h.sumsq_in; p.sumsq_in_n = h.sumsq_in_n; p.sumsq_out = h.sumsq_out; p.eps = eps;
+        p.sumsq_in = h.sumsq_in; p.sumsq_in_n = h.sumsq_in_n; p.sumsq_out = h.sumsq_out; p.eps = eps; p.dbg = nullptr; p.dbg_slot = 0; p.w_evict_first = 0;
         p.tiles_n = (h.N + BM - 1) / BM; p.KB = (h.K + BK - 1) / BK; p.units = p.tiles_n * p.KB;
         p.chunk = (p.units + grid - 1) / grid;
         int rc;

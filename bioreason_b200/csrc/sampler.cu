@@ -256,7 +256,9 @@ __global__ void __launch_bounds__(1024) sampler_kernel(const float* __restrict__
 
 __global__ void advance_kernel(int* step, int* cur_len, int R) {
     const int i = threadIdx.x;
-    br::launch_dependents();
+    // NO early launch_dependents() here: this kernel is the token-step boundary.  Later kernels of the chain (the fused decode
+    // attention) read cur_len BEFORE their own dependency wait; keeping the implicit trigger at completion guarantees that nothing
+    // of step N+1 starts before cur_len of step N is final (and, transitively, before every kernel of step N has completed).
     br::grid_dep_wait();
     if (i < R) atomicAdd(cur_len + i, 1);
     if (i == 0 && step) atomicAdd(step, 1);

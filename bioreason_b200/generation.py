@@ -43,7 +43,12 @@ class SamplingParams:
             return default
         eos = pick("eos_token_id", getattr(model_cfg, "eos_token_id", None))
         if isinstance(eos, (list, tuple)):
-            eos = eos[0]
+            uniq = sorted(set(int(e) for e in eos))
+            if len(uniq) > 1:
+                # HF stops a row on ANY of the ids; the sampler kernel tracks one.  Refuse instead of silently keeping the first.
+                raise NotImplementedError(f"generate(): {len(uniq)} distinct eos_token_id values {uniq}; the decode kernels stop on a single id "
+                                          "(the reference trainer masks on processing_class.eos_token_id, grpo_trainer.py:605) -- pass that one")
+            eos = uniq[0] if uniq else None
         pad = pick("pad_token_id", getattr(model_cfg, "pad_token_id", None))
         if pad is None:
             pad = eos if eos is not None else 0
@@ -143,13 +148,19 @@ class RolloutEngine:
         B, P = input_ids.shape
         C = params.max_new_tokens
 
-        # ---- one host sync: grouping flags + prompt lengths
+        # ---- one host sync: grouping flags + prompt lengths + the layout check (left-padded rows, one contiguous run of ones ending at
+        #      the last column: what `padding_side="left"` produces, grpo_trainer.py:556-565; KV placement and the first-token logits
+        #      below assume it, so anything else is refused instead of generating from a pad position)
         eq = detect_group_size(input_ids, dna_tokenized, batch_idx_map)
         lens = attention_mask.sum(dim=1)
-        host = torch.cat([eq.long(), lens]).tolist()
+        m01 = attention_mask != 0
+        layout_ok = (m01[:, -1].all() & (m01[:, 1:] >= m01[:, :-1]).all()).long().reshape(1) if P > 1 else m01[:, -1].all().long().reshape(1)
+        host = torch.cat([eq.long(), lens, layout_ok]).tolist()
+        if not host[2 * B]:
+            raise ValueError("generate(): attention_mask must be left-padded (each row: zeros, then ones up to the last column)")
         G = group_size_from_flags([bool(x) for x in host[:B]])
         U = B // G
-        plen = [int(x) for x in host[B:]][::G]                           # prompt length of each unique row
+        plen = [int(x) for x in host[B:2 * B]][::G]                      # prompt length of each unique row
 
         # ---- encode + prefill the unique prompts only
         uid = torch.arange(0, B, G, device=dev)

@@ -57,5 +57,8 @@ def test_sampling_params_from_hf_kwargs():
     gc = GenerationConfig(max_new_tokens=9, do_sample=True, temperature=0.6, top_p=0.95, top_k=20, pad_token_id=3)   # grpo_trainer.py:384-391
     p = SamplingParams.from_hf_kwargs(cfg, dict(generation_config=gc))
     assert (p.max_new_tokens, p.do_sample, p.top_k, p.pad_token_id, p.eos_token_id) == (9, True, 20, 3, 7)
-    p = SamplingParams.from_hf_kwargs(cfg, dict(generation_config=gc, max_new_tokens=4, eos_token_id=[11, 12]))   # loose kwargs win
+    p = SamplingParams.from_hf_kwargs(cfg, dict(generation_config=gc, max_new_tokens=4, eos_token_id=[11, 11]))   # loose kwargs win
     assert p.max_new_tokens == 4 and p.eos_token_id == 11
+    import pytest
+    with pytest.raises(NotImplementedError, match="distinct eos_token_id"):                                        # never silently keep eos[0]
+        SamplingParams.from_hf_kwargs(cfg, dict(eos_token_id=[11, 12]))
