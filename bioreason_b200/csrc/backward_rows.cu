@@ -216,14 +216,29 @@ __global__ void transpose_kernel(const bf16* __restrict__ in, long long ldi, bf1
     }
 }
 
-// out[n] (+)= sum_m in[m, n]  (fp32 out)
-__global__ void colsum_kernel(const bf16* __restrict__ in, long long ldi, float* __restrict__ out, int M, int N, int rows_per_cta) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    const int m_lo = blockIdx.y * rows_per_cta, m_hi = min(M, m_lo + rows_per_cta);
-    float s = 0.f;
-    for (int m = m_lo; m < m_hi; ++m) s += __bfloat162float(in[(long long)m * ldi + n]);
-    atomicAdd(out + n, s);
+// out[n] += sum_m in[m, n]  (fp32 out).  CTA = 32 columns x 8 row groups; each row group sums its rows in order, the 8 partials
+// are added in a fixed order through shared memory: no atomics, bit-reproducible.
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ in, long long ldi, float* __restrict__ out, int M, int N) {
+    __shared__ float part[8][32];
+    const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + c;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (n < N) {
+        int m = g;
+        for (; m + 24 < M; m += 32) {                      // 4 independent loads in flight per thread
+            s0 += __bfloat162float(in[(long long)m * ldi + n]); s1 += __bfloat162float(in[(long long)(m + 8) * ldi + n]);
+            s2 += __bfloat162float(in[(long long)(m + 16) * ldi + n]); s3 += __bfloat162float(in[(long long)(m + 24) * ldi + n]);
+        }
+        for (; m < M; m += 8) s0 += __bfloat162float(in[(long long)m * ldi + n]);
+    }
+    part[g][c] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (g == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += part[i][c];
+        out[n] += t;
+    }
 }
 
 }  // namespace
@@ -288,9 +303,7 @@ int br_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int M
 
 int br_colsum_accumulate(const void* in, int64_t ldi, float* out, int M, int N, void* stream) {
     BR_CHECK_ARG(M > 0 && N > 0, "colsum: empty");
-    const int rows_per_cta = 512;
-    dim3 grid((N + 255) / 256, (M + rows_per_cta - 1) / rows_per_cta);
-    colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)in, ldi, out, M, N, rows_per_cta);
+    colsum_kernel<<<(N + 31) / 32, 256, 0, (cudaStream_t)stream>>>((const bf16*)in, ldi, out, M, N);
     BR_CHECK_LAUNCH();
     return BR_OK;
 }

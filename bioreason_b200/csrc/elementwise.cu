@@ -109,15 +109,17 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, cons
 // mode 0 (Qwen3): x = w * bf16(x * rstd) (if w), then bf16-rounded rotate-half RoPE with bf16 cos/sin (HF rounding points)
 // mode 1 (ESM)  : x = x * qscale (q heads only), then fp32 RoPE with one final rounding
 template <int D>
-__global__ void qk_rope_kernel(bf16* __restrict__ qkv, long long ld, int M, int n_q, int n_k, const bf16* __restrict__ qw,
-                               const bf16* __restrict__ kw, const int* __restrict__ pos, float theta, float eps, float qscale, int mode) {
+__global__ void qk_rope_kernel(bf16* qkv, long long ld, int M, int n_q, int n_k, const bf16* __restrict__ qw,
+                               const bf16* __restrict__ kw, const int* __restrict__ pos, float theta, float eps, float qscale, int mode,
+                               bf16* out, long long ldo, const float2* __restrict__ rope, int rope_n_pos) {
     constexpr int E = D / 64;
     const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int heads = n_q + n_k;
     if (wid >= M * heads) return;
     const int m = wid / heads, h = wid % heads;
-    bf16* p = qkv + (long long)m * ld + (long long)h * D;
+    const bf16* p = qkv + (long long)m * ld + (long long)h * D;
+    bf16* o = out ? out + (long long)m * ldo + (long long)h * D : qkv + (long long)m * ld + (long long)h * D;
     float lo[E], hi[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) { lo[e] = __bfloat162float(p[lane * E + e]); hi[e] = __bfloat162float(p[D / 2 + lane * E + e]); }
@@ -138,13 +140,18 @@ __global__ void qk_rope_kernel(bf16* __restrict__ qkv, long long ld, int M, int 
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int j = lane * E + e;
-            const float inv_freq = 1.0f / powf(theta, (float)(2 * j) / (float)D);
             float sn, cs;
-            sincosf(position * inv_freq, &sn, &cs);
-            sn = rbf(sn); cs = rbf(cs);
+            if (rope && pos[m] < rope_n_pos) {                       // table built once by br_rope_table (same arithmetic, bf16-rounded)
+                const float2 t = __ldg(rope + (long long)pos[m] * (D / 2) + j);
+                cs = t.x; sn = t.y;
+            } else {
+                const float inv_freq = 1.0f / powf(theta, (float)(2 * j) / (float)D);
+                sincosf(position * inv_freq, &sn, &cs);
+                sn = rbf(sn); cs = rbf(cs);
+            }
             const float a = lo[e], b = hi[e];
-            p[j] = __float2bfloat16(rbf(a * cs) + rbf(-b * sn));
-            p[D / 2 + j] = __float2bfloat16(rbf(b * cs) + rbf(a * sn));
+            o[j] = __float2bfloat16(rbf(a * cs) + rbf(-b * sn));
+            o[D / 2 + j] = __float2bfloat16(rbf(b * cs) + rbf(a * sn));
         }
     } else {
         const float sc = (h < n_q) ? qscale : 1.f;
@@ -155,8 +162,8 @@ __global__ void qk_rope_kernel(bf16* __restrict__ qkv, long long ld, int M, int 
             float sn, cs;
             sincosf(position * inv_freq, &sn, &cs);
             const float a = rbf(lo[e] * sc), b = rbf(hi[e] * sc);
-            p[j] = __float2bfloat16(a * cs - b * sn);
-            p[D / 2 + j] = __float2bfloat16(b * cs + a * sn);
+            o[j] = __float2bfloat16(a * cs - b * sn);
+            o[D / 2 + j] = __float2bfloat16(b * cs + a * sn);
         }
     }
 }
@@ -258,20 +265,30 @@ int br_layernorm(const void* x, int64_t ldx, const void* w, const void* b, void*
     return BR_OK;
 }
 
-int br_qk_rope(void* qkv, int64_t ld, int M, int n_q_heads, int n_k_heads, int head_dim, const void* q_norm_w, const void* k_norm_w,
-               const int32_t* positions, float theta, float eps, float q_scale, int mode, void* stream) {
+int br_qk_rope_ex(void* qkv, int64_t ld, void* out, int64_t ldo, int M, int n_q_heads, int n_k_heads, int head_dim, const void* q_norm_w,
+                  const void* k_norm_w, const int32_t* positions, float theta, float eps, float q_scale, int mode, const float* rope_table,
+                  int rope_n_pos, void* stream) {
     BR_CHECK_ARG(M > 0 && (head_dim == 128 || head_dim == 64), "qk_rope: head_dim must be 64 or 128 (got %d)", head_dim);
+    BR_CHECK_ARG(!(rope_table && mode != 0), "qk_rope: the cos/sin table holds the bf16-rounded Qwen3 values (mode 0) only");
+    BR_CHECK_ARG(!out || ldo % 8 == 0, "qk_rope: ldo %% 8");
     const long long warps = (long long)M * (n_q_heads + n_k_heads);
     const int wpb = 8;
     const unsigned grid = (unsigned)((warps + wpb - 1) / wpb);
     if (head_dim == 128)
         qk_rope_kernel<128><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((bf16*)qkv, ld, M, n_q_heads, n_k_heads, (const bf16*)q_norm_w,
-                                                                         (const bf16*)k_norm_w, positions, theta, eps, q_scale, mode);
+                                                                         (const bf16*)k_norm_w, positions, theta, eps, q_scale, mode,
+                                                                         (bf16*)out, ldo, (const float2*)rope_table, rope_n_pos);
     else
         qk_rope_kernel<64><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>((bf16*)qkv, ld, M, n_q_heads, n_k_heads, (const bf16*)q_norm_w,
-                                                                        (const bf16*)k_norm_w, positions, theta, eps, q_scale, mode);
+                                                                        (const bf16*)k_norm_w, positions, theta, eps, q_scale, mode,
+                                                                        (bf16*)out, ldo, (const float2*)rope_table, rope_n_pos);
     BR_CHECK_LAUNCH();
     return BR_OK;
+}
+
+int br_qk_rope(void* qkv, int64_t ld, int M, int n_q_heads, int n_k_heads, int head_dim, const void* q_norm_w, const void* k_norm_w,
+               const int32_t* positions, float theta, float eps, float q_scale, int mode, void* stream) {
+    return br_qk_rope_ex(qkv, ld, nullptr, 0, M, n_q_heads, n_k_heads, head_dim, q_norm_w, k_norm_w, positions, theta, eps, q_scale, mode, nullptr, 0, stream);
 }
 
 int br_embed_gather(const int64_t* ids, const void* table, int64_t ldt, int64_t vocab, void* out, int64_t ldo, int M, int d, const int32_t* keep,

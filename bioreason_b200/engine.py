@@ -69,8 +69,10 @@ class LayerSaved:
     h_in: torch.Tensor = None
     rstd1: torch.Tensor = None
     xn1: torch.Tensor = None
-    qkv: torch.Tensor = None          # post qk-norm + RoPE
-    qkv_pre: torch.Tensor = None      # pre-norm q/k (for the qk-norm backward)
+    q: torch.Tensor = None            # post qk-norm + RoPE (views of one [M, (Hq+Hkv)D] buffer)
+    k: torch.Tensor = None
+    v: torch.Tensor = None            # view of the QKV GEMM output
+    qkv_pre: torch.Tensor = None      # the QKV GEMM output itself: pre-norm q/k (for the qk-norm backward) | v
     attn: torch.Tensor = None
     lse: torch.Tensor = None
     h_mid: torch.Tensor = None
@@ -82,6 +84,18 @@ class LayerSaved:
     t_o: torch.Tensor = None
     t_gu: torch.Tensor = None
     t_down: torch.Tensor = None
+
+
+_ROPE_TABLES = {}
+
+
+def _rope_table(n_pos: int, D: int, theta: float, device):
+    """(cos, sin) pairs of positions [0, n_pos), bf16-rounded like HF's rotary tables; cached per (device, D, theta), grown on demand."""
+    key = (str(device), D, float(theta))
+    t = _ROPE_TABLES.get(key)
+    if t is None or t.shape[0] < n_pos:
+        t = _ROPE_TABLES[key] = ops.rope_table(max(n_pos, 4096), D, theta, device)
+    return t
 
 
 def _lin(x, w, *, lora_a=None, lora_b=None, lora_scale=1.0, saved_t=None, **kw):
@@ -104,6 +118,8 @@ def decoder_forward(W: DecoderW, h: torch.Tensor, B: int, L: int, positions: tor
     eps = cfg.rms_norm_eps
     theta = cfg.rope_parameters["rope_theta"] if hasattr(cfg, "rope_parameters") else cfg.rope_theta
     qo, ko, vo = 0, Hq * D, (Hq + Hkv) * D
+    assert saved is None or kv_sink is None, "the KV sink reads roped K|V from the fused buffer; the training path keeps that buffer pre-norm"
+    rope = _rope_table(L, D, theta, h.device)                          # cos/sin of positions 0..L-1, built once per (L, theta)
     for li, Lw in enumerate(W.layers):
         lw = lora.layers[li] if lora is not None else None
         ls = lora.scale if lora is not None else 1.0
@@ -115,15 +131,21 @@ def decoder_forward(W: DecoderW, h: torch.Tensor, B: int, L: int, positions: tor
             xn = ops.rmsnorm(h, Lw.ln1, eps)
         qkv, t = _lin(xn, Lw.w_qkv, lora_a=lw.a_qkv if lw else None, lora_b=lw.b_qkv if lw else None, lora_scale=ls)
         if S is not None:
+            # training: the roped q|k go to their own buffer, the GEMM output keeps the pre-norm q|k (qk-norm backward) and V -- no copy
             S.t_qkv = t
-            S.qkv_pre = qkv[:, :vo].clone()
-        ops.qk_rope_(qkv, Hq, Hkv, D, positions, theta, q_norm_w=Lw.q_norm, k_norm_w=Lw.k_norm, eps=eps, mode=0)
+            S.qkv_pre = qkv
+            qk = torch.empty(h.shape[0], vo, device=h.device, dtype=torch.bfloat16)
+            ops.qk_rope_(qkv, Hq, Hkv, D, positions, theta, q_norm_w=Lw.q_norm, k_norm_w=Lw.k_norm, eps=eps, mode=0, out=qk, rope=rope)
+            q, k, v = qk[:, qo:ko], qk[:, ko:vo], qkv[:, vo:]
+            S.q, S.k, S.v = q, k, v
+        else:
+            ops.qk_rope_(qkv, Hq, Hkv, D, positions, theta, q_norm_w=Lw.q_norm, k_norm_w=Lw.k_norm, eps=eps, mode=0, rope=rope)
+            q, k, v = qkv[:, qo:ko], qkv[:, ko:vo], qkv[:, vo:]
         if kv_sink is not None:
             kv_sink(li, qkv)
-        q, k, v = qkv[:, qo:ko], qkv[:, ko:vo], qkv[:, vo:]
         if S is not None:
             attn, lse = ops.attn_fwd(q, k, v, B, L, Hq, Hkv, D, kv_start=kv_start, kv_end=kv_end, causal=True, want_lse=True)
-            S.qkv, S.attn, S.lse = qkv, attn, lse
+            S.attn, S.lse = attn, lse
         else:
             attn = ops.attn_fwd(q, k, v, B, L, Hq, Hkv, D, kv_start=kv_start, kv_end=kv_end, causal=True)
         h2, t = _lin(attn, Lw.w_o, lora_a=lw.a_o if lw else None, lora_b=lw.b_o if lw else None, lora_scale=ls, residual=h)

@@ -28,6 +28,29 @@ _TEXT_ALIASES = {"Qwen/Qwen3-4B": "qwen3-4b", "Qwen/Qwen3-1.7B": "qwen3-1.7b"}
 _DNA_ALIASES = {"InstaDeepAI/nucleotide-transformer-v2-500m-multi-species": "nt-v2-500m"}
 
 
+def _config_from_dir(path: str, kind: str):
+    """config.json of a local HF checkpoint directory -> the config object the kernels are built from (no hub access)."""
+    import json
+    from transformers import EsmConfig, Qwen3Config
+    raw = json.load(open(os.path.join(path, "config.json")))
+    if kind == "text":
+        cfg = Qwen3Config(**{k: v for k, v in raw.items() if k not in ("architectures", "model_type", "transformers_version", "torch_dtype", "auto_map")})
+        if getattr(cfg, "dna_token_ids", None) is None:
+            from ..configs import DNA_END_ID, DNA_PAD_ID, DNA_START_ID
+            cfg.dna_token_ids = (DNA_START_ID, DNA_PAD_ID, DNA_END_ID)
+        if cfg.pad_token_id is None:
+            cfg.pad_token_id = cfg.eos_token_id if not isinstance(cfg.eos_token_id, (list, tuple)) else cfg.eos_token_id[0]
+        cfg._attn_implementation = "sdpa"
+        return cfg
+    cfg = EsmConfig(**{k: v for k, v in raw.items() if k not in ("architectures", "model_type", "transformers_version", "torch_dtype", "auto_map")})
+    cfg.gated_mlp = True                                                    # NT-v2 (SURVEY.md §8.0); plain ESM FFNs are not on this path
+    cfg.add_bias_fc = bool(raw.get("add_bias_fc", False))
+    if getattr(cfg, "cls_token_id", None) is None:
+        cfg.cls_token_id = 3
+    cfg._attn_implementation = "sdpa"
+    return cfg
+
+
 class LazyCausalLMOutput:
     """`.logits` ([B, L, V]) is computed on first access; `.loss` comes from the fused CE kernel."""
 
@@ -62,8 +85,11 @@ class DNALLMModel(nn.Module):
         self.max_length_dna, self.max_length_text = max_length_dna, max_length_text
         self.dna_is_evo2, self.dna_embedding_layer = dna_is_evo2, dna_embedding_layer
         self.warnings_issued = {}                                           # grpo_trainer.py:411 writes into it
-        text_model, dna_model = self._build_modules(text_model_name, dna_model_name, cache_dir, seed)
+        self._local_dirs = []
+        text_model, dna_model = self._build_modules(text_model_name, dna_model_name, cache_dir, seed, self._local_dirs)
         self.text_model, self.dna_model = text_model, dna_model
+        # back-reference for compat/peft.get_peft_model(model.text_model, ...) (reason.py:386): plain attribute, not a submodule
+        object.__setattr__(text_model, "_b200_owner", __import__("weakref").ref(self))
         self.text_config, self.dna_config = text_model.config, dna_model.config
         self.config = self.text_config                                      # grpo_trainer.py:472 touches model.config
         self.text_tokenizer = self.dna_tokenizer = self.processor = None    # no tokenizer files offline
@@ -86,22 +112,31 @@ class DNALLMModel(nn.Module):
         self._proj_grad_w = torch.zeros_like(self.dna_projection.weight, dtype=torch.float32)
         self._proj_grad_b = torch.zeros_like(self.dna_projection.bias, dtype=torch.float32)
         self.sync_projection()
+        for prefix, path in self._local_dirs:                               # local HF checkpoint directories (dna_llm.py:57-68)
+            from .. import checkpoint
+            sd = {prefix + k: v for k, v in checkpoint.read_hf_dir(path).items()}
+            mapped, _ = checkpoint.normalize_keys(sd, self.state_dict().keys())
+            self.load_weights(mapped)
+
+    @property
+    def text(self):
+        """reason.py:89 walks `model.text.named_modules()`."""
+        return self.text_model
 
     # ------------------------------------------------------------------ construction helpers
     @staticmethod
-    def _build_modules(text_name, dna_name, cache_dir, seed):
+    def _build_modules(text_name, dna_name, cache_dir, seed, local_dirs):
         from transformers import EsmForMaskedLM, Qwen3ForCausalLM
-        def resolve(name, aliases, factory):
+        def resolve(name, aliases, factory, kind):
             if not isinstance(name, str):
                 return name                                                  # a config object
-            if os.path.isdir(name):
-                return None                                                  # local checkpoint directory
+            if os.path.isdir(name):                                          # local HF checkpoint directory: config.json + weights
+                local_dirs.append(("text_model." if kind == "text" else "dna_model.", name))
+                return _config_from_dir(name, kind)
             key = aliases.get(name, name)
             return factory(key)
-        tcfg = resolve(text_name, _TEXT_ALIASES, _text_config)
-        dcfg = resolve(dna_name, _DNA_ALIASES, _dna_config)
-        if tcfg is None or dcfg is None:
-            raise NotImplementedError("loading local checkpoints: SURVEY.md §8f rank 4 (checkpoint interop)")
+        tcfg = resolve(text_name, _TEXT_ALIASES, _text_config, "text")
+        dcfg = resolve(dna_name, _DNA_ALIASES, _dna_config, "dna")
         # seeded random init at the real shapes (no weights exist offline); built directly on the GPU in bf16
         dt = torch.get_default_dtype()
         try:
@@ -131,13 +166,28 @@ class DNALLMModel(nn.Module):
         self.load_weights({k: v for k, v in oracle_model.state_dict().items()})
         return self
 
+    def load_state_dict(self, state_dict, strict: bool = False, assign: bool = False):
+        """torch's signature; accepts every checkpoint layout the reference's scripts read (reason.py:448-537, see checkpoint.py) and
+        refreshes the kernel-layout copies.  Returns the usual (missing_keys, unexpected_keys) pair."""
+        from .. import checkpoint
+        return checkpoint.load_into(self, state_dict, strict=strict)
+
+    def load_checkpoint(self, path):
+        """A PyTorch file (raw / Lightning / DeepSpeed state dict), a peft adapter directory or a HF model directory."""
+        from .. import checkpoint
+        return checkpoint.load_into(self, path)
+
     def load_weights(self, state_dict: Dict[str, torch.Tensor]):
-        """load_state_dict(strict=False) that tolerates the NT-v2 FFN layout and refreshes kernel-layout copies."""
+        """load_state_dict(strict=False) that tolerates the NT-v2 FFN layout and refreshes kernel-layout copies.
+        Returns the list of this model's keys the dict did not cover."""
         own = self.state_dict()
+        seen = set()
         with torch.no_grad():
             for k, v in state_dict.items():
                 if k in own and own[k].shape == v.shape:
-                    own[k].copy_(v.to(own[k].dtype))
+                    own[k].copy_(v.to(device=own[k].device, dtype=own[k].dtype))
+                    seen.add(k)
+        missing = [k for k in own if k not in seen and "inv_freq" not in k and "position_ids" not in k]
         # the encoder's interleaved gate/up copy and the projector compute copy are derived -> rebuild
         F = self.dna_config.intermediate_size
         with torch.no_grad():
@@ -147,7 +197,13 @@ class DNALLMModel(nn.Module):
                 gv.copy_(w[:F].view(F // 8, 8, -1)); uv.copy_(w[F:].view(F // 8, 8, -1))
         refresh_decoder_gu(self.text_model, self._dec)
         self._rollout_dec = None
+        if getattr(self, "_rollout", None) is not None:
+            self._rollout._cached.clear()
         self.sync_projection()
+        if self._lora is not None:
+            self._dec.build_transposes()
+            self.sync_adapters(rollout=False)
+        return missing
 
     def sync_projection(self):
         """bf16 compute copy of the (fp32 master) projector; call after every optimizer step."""
@@ -170,6 +226,26 @@ class DNALLMModel(nn.Module):
         self._proj_ref = (self._proj_w16.clone(), self._proj_b16.clone())    # the reference policy's projector (deep copy at init)
         self._dec.build_transposes()
         return self._lora
+
+    @torch.no_grad()
+    def merge_and_unload_lora(self):
+        """peft's `merge_and_unload()` (reason.py:443-446): W <- W + (alpha/r) B A for every adapted projection, then drop the adapters
+        (the merged model becomes the new frozen base / reference policy)."""
+        if self._lora is None:
+            return
+        from ..lora import TARGETS
+        s = self._lora.scale
+        for layer, mods in zip(self.text_model.model.layers, self._lora.modules):
+            for parent, names in ((layer.self_attn, TARGETS[:4]), (layer.mlp, TARGETS[4:])):
+                for n in names:
+                    ll = mods[n]
+                    w = ll.base_layer.weight
+                    w.data.add_((s * (ll.lora_B["default"].weight.float() @ ll.lora_A["default"].weight.float())).to(w.dtype))
+                    setattr(parent, n, ll.base_layer)
+        self._lora, self._proj_ref, self._rollout_dec = None, None, None
+        if getattr(self, "_rollout", None) is not None:
+            self._rollout._cached.clear()
+        refresh_decoder_gu(self.text_model, self._dec)                      # gate/up kernel copy + stale transposes
 
     def trainable_parameters(self):
         ps = list(self._lora.params) if self._lora is not None else []

@@ -177,13 +177,15 @@ def layernorm(x, w, b, eps: float, out=None):
     return out
 
 
-def qk_rope_(qkv, n_q, n_k, head_dim, positions, theta, *, q_norm_w=None, k_norm_w=None, eps=1e-6, q_scale=1.0, mode=0):
-    """In place on the fused QKV buffer [M, >= (n_q+n_k)*head_dim]."""
+def qk_rope_(qkv, n_q, n_k, head_dim, positions, theta, *, q_norm_w=None, k_norm_w=None, eps=1e-6, q_scale=1.0, mode=0, out=None, rope=None):
+    """On the fused QKV buffer [M, >= (n_q+n_k)*head_dim]: in place, or (out=) into a separate [M, >= (n_q+n_k)*head_dim] buffer so the
+    pre-norm values stay available for the backward.  rope: optional cos/sin table from rope_table() (decoder rows, mode 0)."""
     _need_cuda(qkv, positions)
     assert positions.dtype == torch.int32 and positions.numel() == qkv.shape[0]
-    check(lib().br_qk_rope(ptr(qkv), _row_major_2d(qkv), qkv.shape[0], n_q, n_k, head_dim, ptr(q_norm_w), ptr(k_norm_w),
-                           ptr(positions, "int32_t*"), float(theta), float(eps), float(q_scale), mode, _stream()), "qk_rope")
-    return qkv
+    check(lib().br_qk_rope_ex(ptr(qkv), _row_major_2d(qkv), ptr(out), _row_major_2d(out) if out is not None else 0, qkv.shape[0], n_q, n_k, head_dim,
+                              ptr(q_norm_w), ptr(k_norm_w), ptr(positions, "int32_t*"), float(theta), float(eps), float(q_scale), mode,
+                              ptr(rope, "float*"), rope.shape[0] if rope is not None else 0, _stream()), "qk_rope")
+    return qkv if out is None else out
 
 
 def embed_gather(ids, table, keep=None, out=None):
@@ -406,6 +408,30 @@ def xty_accumulate_(out, big, small, *, P=None, chunk_stride=1, chunk_offset=0, 
     check(lib().br_xty_accumulate(ptr(big), _row_major_2d(big), ptr(small), _row_major_2d(small), ptr(out, "float*"), out.stride(0), M, P, Rr,
                                   chunk_stride, chunk_offset, 1 if transpose_out else 0, _stream()), "xty_accumulate")
     return out
+
+
+_LORA_WS = {}
+
+
+def lora_grad_tn(big, small, segs, *, mode=0):
+    """Deterministic tcgen05 TN GEMM: product[P, N] = big[M, P]^T @ small[M, N]; the blocks named by `segs` are ADDED into fp32 views.
+    segs: list of (dst fp32 2-D view with contiguous rows, row_lo, row_hi, col_lo, n_cols); mode 1: one segment, dst[n, p] (transposed);
+    mode 2: gate/up-blocked product rows (segment 0 = gate rows, 1 = up rows)."""
+    _need_cuda(big, small)
+    assert big.dtype == torch.bfloat16 and small.dtype == torch.bfloat16 and big.shape[0] == small.shape[0]
+    M, P = big.shape
+    N = small.shape[1]
+    dev = big.device
+    ws = _LORA_WS.get(dev)
+    if ws is None:
+        ws = _LORA_WS[dev] = torch.zeros(lib().br_lora_grad_workspace_bytes(), device=dev, dtype=torch.uint8)
+    arr = ffi.new("br_lora_grad_seg[]", len(segs))
+    for i, (dst, row_lo, row_hi, col_lo, n_cols) in enumerate(segs):
+        assert dst.dtype == torch.float32 and dst.dim() == 2 and dst.stride(1) == 1
+        arr[i].dst = ptr(dst, "float*"); arr[i].ld = dst.stride(0)
+        arr[i].row_lo, arr[i].row_hi, arr[i].col_lo, arr[i].n_cols = int(row_lo), int(row_hi), int(col_lo), int(n_cols)
+    check(lib().br_lora_grad_tn(ptr(big), _row_major_2d(big), ptr(small), _row_major_2d(small), M, P, N, int(mode), arr, len(segs), ptr(ws),
+                                _stream()), "lora_grad_tn")
 
 
 def transpose(x, out=None, pad_cols_to: int = 8):

@@ -107,18 +107,19 @@ def policy_backward(model, ctx: PolicyCtx, dlogp: torch.Tensor):
         # ---------------- MLP: h_out = h_mid + down(act)
         if lora:
             dact, u = lin_bwd(dh, Lw.w_down_T, S.act, S.t_down, li, ("down_proj",), Tl["a_down_T"], Tl["b_down_T"])
-            ops.xty_accumulate_(lora.grad_view(li, "down_proj", "B"), dh, S.t_down)                  # dB = dy^T t
-            ops.xty_accumulate_(lora.grad_view(li, "down_proj", "A"), S.act, u, transpose_out=True)  # dA = u^T x
+            ops.lora_grad_tn(dh, S.t_down, [(lora.grad_view(li, "down_proj", "B"), 0, d, 0, r)])               # dB = dy^T t
+            ops.lora_grad_tn(S.act, u, [(lora.grad_view(li, "down_proj", "A"), 0, F, 0, r)], mode=1)           # dA = u^T x
         else:
             dact = ops.gemm(dh, Lw.w_down_T)
         dgu = ops.swiglu_bwd(S.gu, dact)
         del dact
         if lora:
             dxn2, u = lin_bwd(dgu, Lw.w_gu_T, S.xn2, S.t_gu, li, ("gate_proj", "up_proj"), Tl["a_gu_T"], Tl["b_gu_T"])
-            ops.xty_accumulate_(lora.grad_view(li, "gate_proj", "B"), dgu, S.t_gu[:, :r], P=F, chunk_stride=2, chunk_offset=0)
-            ops.xty_accumulate_(lora.grad_view(li, "up_proj", "B"), dgu, S.t_gu[:, r:], P=F, chunk_stride=2, chunk_offset=1)
-            ops.xty_accumulate_(lora.grad_view(li, "gate_proj", "A"), S.xn2, u[:, :r], transpose_out=True)
-            ops.xty_accumulate_(lora.grad_view(li, "up_proj", "A"), S.xn2, u[:, r:], transpose_out=True)
+            # one product dgu^T [2F] x t_gu [2r]: gate rows keep their r columns, up rows theirs (cross blocks are discarded)
+            ops.lora_grad_tn(dgu, S.t_gu, [(lora.grad_view(li, "gate_proj", "B"), 0, 2 * F, 0, r),
+                                           (lora.grad_view(li, "up_proj", "B"), 0, 2 * F, r, r)], mode=2)
+            ops.lora_grad_tn(S.xn2, u[:, :r], [(lora.grad_view(li, "gate_proj", "A"), 0, d, 0, r)], mode=1)
+            ops.lora_grad_tn(S.xn2, u[:, r:], [(lora.grad_view(li, "up_proj", "A"), 0, d, 0, r)], mode=1)
         else:
             dxn2 = ops.gemm(dgu, Lw.w_gu_T)
         del dgu
@@ -127,21 +128,22 @@ def policy_backward(model, ctx: PolicyCtx, dlogp: torch.Tensor):
         # ---------------- attention: h_mid = h_in + o_proj(attn)
         if lora:
             dattn, u = lin_bwd(dh_mid, Lw.w_o_T, S.attn, S.t_o, li, ("o_proj",), Tl["a_o_T"], Tl["b_o_T"])
-            ops.xty_accumulate_(lora.grad_view(li, "o_proj", "B"), dh_mid, S.t_o)
-            ops.xty_accumulate_(lora.grad_view(li, "o_proj", "A"), S.attn, u, transpose_out=True)
+            ops.lora_grad_tn(dh_mid, S.t_o, [(lora.grad_view(li, "o_proj", "B"), 0, d, 0, r)])
+            ops.lora_grad_tn(S.attn, u, [(lora.grad_view(li, "o_proj", "A"), 0, Hq * D, 0, r)], mode=1)
         else:
             dattn = ops.gemm(dh_mid, Lw.w_o_T)
         dqkv = torch.empty(M, (Hq + 2 * Hkv) * D, device=dev, dtype=torch.bfloat16)
-        qkv = S.qkv
-        ops.attn_bwd(qkv[:, qo:ko], qkv[:, ko:vo], qkv[:, vo:], S.attn, dattn, S.lse, dqkv[:, qo:ko], dqkv[:, ko:vo], dqkv[:, vo:],
+        ops.attn_bwd(S.q, S.k, S.v, S.attn, dattn, S.lse, dqkv[:, qo:ko], dqkv[:, ko:vo], dqkv[:, vo:],
                      B, L, Hq, Hkv, D, kv_start=ctx.ks, kv_end=ctx.ke)
         del dattn
         ops.qk_rope_bwd_(dqkv, S.qkv_pre, Hq, Hkv, D, Lw.q_norm, Lw.k_norm, ctx.pos, theta, eps)
         if lora:
             dxn1, u = lin_bwd(dqkv, Lw.w_qkv_T, S.xn1, S.t_qkv, li, ("q_proj", "k_proj", "v_proj"), Tl["a_qkv_T"], Tl["b_qkv_T"])
-            for j, (name, lo, hi) in enumerate((("q_proj", qo, ko), ("k_proj", ko, vo), ("v_proj", vo, vo + Hkv * D))):
-                ops.xty_accumulate_(lora.grad_view(li, name, "B"), dqkv[:, lo:hi], S.t_qkv[:, j * r:(j + 1) * r])
-                ops.xty_accumulate_(lora.grad_view(li, name, "A"), S.xn1, u[:, j * r:(j + 1) * r], transpose_out=True)
+            # one product dqkv^T [(Hq+2Hkv)D] x t_qkv [3r]: the q / k / v row blocks keep their own r columns
+            ops.lora_grad_tn(dqkv, S.t_qkv, [(lora.grad_view(li, "q_proj", "B"), qo, ko, 0, r), (lora.grad_view(li, "k_proj", "B"), ko, vo, r, r),
+                                             (lora.grad_view(li, "v_proj", "B"), vo, vo + Hkv * D, 2 * r, r)])
+            for j, name in enumerate(("q_proj", "k_proj", "v_proj")):
+                ops.lora_grad_tn(S.xn1, u[:, j * r:(j + 1) * r], [(lora.grad_view(li, name, "A"), 0, d, 0, r)], mode=1)
         else:
             dxn1 = ops.gemm(dqkv, Lw.w_qkv_T)
         del dqkv

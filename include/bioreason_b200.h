@@ -95,6 +95,11 @@ int br_layernorm(const void* x, int64_t ldx, const void* w, const void* b, void*
  * arange over the padded row in forward() and cumsum(mask)-1 in generate()). */
 int br_qk_rope(void* qkv, int64_t ld, int M, int n_q_heads, int n_k_heads, int head_dim, const void* q_norm_w,
                const void* k_norm_w, const int32_t* positions, float theta, float eps, float q_scale, int mode, void* stream);
+/* same; out != NULL writes the roped q|k heads to out[M, >= (n_q+n_k)*head_dim] instead of in place (the pre-norm values stay in qkv for
+ * the backward: no copy); rope_table (br_rope_table, [n_pos, head_dim/2] (cos, sin) pairs) replaces the per-element powf/sincosf (mode 0) */
+int br_qk_rope_ex(void* qkv, int64_t ld, void* out, int64_t ldo, int M, int n_q_heads, int n_k_heads, int head_dim, const void* q_norm_w,
+                  const void* k_norm_w, const int32_t* positions, float theta, float eps, float q_scale, int mode, const float* rope_table,
+                  int rope_n_pos, void* stream);
 /* out[m] = table[ids[m]] (zeros if keep && !keep[m], or id out of range); ids int64 */
 int br_embed_gather(const int64_t* ids, const void* table, int64_t ldt, int64_t vocab, void* out, int64_t ldo, int M, int d,
                     const int32_t* keep, void* stream);
@@ -212,6 +217,17 @@ int br_qk_rope_bwd(void* dqkv, int64_t ldd, const void* qk_pre, int64_t ldp, int
                    const void* q_norm_w, const void* k_norm_w, const int32_t* positions, float theta, float eps, void* stream);
 /* out[P, Rr] += big[M, P]^T . small[M, Rr] (fp32 atomics; LoRA dA / dB).  big columns are taken in 16-byte chunks
  * (c * chunk_stride + chunk_offset); transpose_out writes out[Rr, P] instead. */
+/* LoRA weight gradients on tcgen05 (deterministic):  product[P, N] = big[M, P]^T . small[M, N] over the M tokens (both token-major,
+ * bf16, read as MN-major tensor-core operands), then  dst (+)= the blocks the segments name.
+ *   mode 0: segment i adds product rows [row_lo, row_hi), columns [col_lo, col_lo + n_cols) into dst[(row - row_lo) * ld + col - col_lo]
+ *           (dB of one adapter, or the q / k / v blocks of the fused qkv product);
+ *   mode 1: one segment, transposed: dst[n * ld + p] += product[p, n]  (dA = u^T x written as [r, in]);
+ *   mode 2: gate/up-blocked rows (16 = 8 gate | 8 up): segment 0 takes the gate rows, segment 1 the up rows -> dst row (p / 16) * 8 + p % 8.
+ * workspace: br_lora_grad_workspace_bytes(), zero-initialised once.  Replaces torch autograd through peft's LoRA Linear (reason.py:362-394). */
+typedef struct br_lora_grad_seg { float* dst; int64_t ld; int32_t row_lo, row_hi, col_lo, n_cols; } br_lora_grad_seg;
+int64_t br_lora_grad_workspace_bytes(void);
+int br_lora_grad_tn(const void* big, int64_t ldb, const void* small, int64_t lds, int M, int P, int N, int mode,
+                    const br_lora_grad_seg* segs, int n_seg, void* workspace, void* stream);
 int br_xty_accumulate(const void* big, int64_t ldb, const void* small, int64_t lds, float* out, int64_t ldo, int M, int P, int Rr,
                       int chunk_stride, int chunk_offset, int transpose_out, void* stream);
 int br_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int M, int N, void* stream);
