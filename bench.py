@@ -269,10 +269,7 @@ def run_b200(args):
     line = {"metric": "GRPO tokens/sec (rollout+update)", "value": round(tokens_per_step / t_step, 2), "unit": "tokens/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_string(args),
-                       "shapes": f"{args.dna}+{args.text}", "rows_per_gpu": B, "parallelism": f"dp{world}",
-                       "l2": "weights (8 GB) and activations (>60 GB) exceed the 126 MB L2 every step; no flush needed",
-                       "weights": "seeded random init (no checkpoints offline)", "build_s": round(t_build, 1)},
+            "config": bench_config(args, world), "build_s": round(t_build, 1),
             "e2e": {"value": round(tokens_per_step / (ms_e2e / args.steps / 1e3), 2), "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
@@ -293,12 +290,31 @@ def run_b200(args):
 # ----------------------------------------------------------------------------------------------------------------
 # CPU reference arm: the reference's HF/PyTorch path (the oracle) on the host cores, bounded sample
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_reference(args, budget_s=25.0):
-    """Times the oracle's building blocks at the REAL widths on a bounded sample (1 row, 1 decoder layer, 1 encoder layer,
-    a few decode steps) and composes the reference's own schedule for one GRPO step (A_ref of SURVEY.md §8d: the reference
-    re-encodes and re-prefills the prompt for each of the G rows and in every pass).  fp32, all host threads."""
+def _fast_init_(module):
+    """Fill every parameter with a tiled block of N(0, 0.02) values (a 4 B-parameter normal_() init alone would take the CPU budget)."""
     import torch
-    from transformers import Qwen3Config
+    g = torch.Generator().manual_seed(0)
+    block = torch.randn(1 << 20, generator=g) * 0.02
+    with torch.no_grad():
+        for p_ in module.parameters():
+            flat = p_.data.view(-1)
+            n = flat.numel()
+            reps = (n + block.numel() - 1) // block.numel()
+            flat.copy_(block.repeat(reps)[:n] if reps > 1 else block[:n])
+        for name, p_ in module.named_parameters():
+            if name.endswith("norm.weight") or name.endswith("layernorm.weight"):
+                p_.data.fill_(1.0)
+
+
+def cpu_reference(args, budget_s=25.0):
+    """The reference's own path (HF Qwen3 / ESM modules, fp32, the oracle's classes) timed on the host cores at the REAL widths AND
+    the real depth on a bounded sample, then composed with the reference's schedule for one GRPO step (A_ref of SURVEY.md §8d: the
+    reference re-encodes and re-prefills the prompt for each of the G rows and in every pass).  Measured at full depth (36 decoder
+    layers): one row of the reference-policy log-prob pass (L = P + C tokens, [L, V] logits included) and cached decode steps for the
+    G rows at context P + C/2; measured on one layer and scaled: the backward (a full-depth fwd+bwd row is ~40 s).  The full-depth
+    forward also validates the composition (`fwd_measured_over_composed`)."""
+    import torch
+    from transformers import DynamicCache
     from transformers.models.qwen3.modeling_qwen3 import Qwen3ForCausalLM
     from bioreason_b200.configs import dna_config, text_config
     from oracle.models import build_dna_model
@@ -320,64 +336,91 @@ def cpu_reference(args, budget_s=25.0):
     P = args.text_len + 2 * args.dna_len
     L = P + C
     nl, nle = tc.num_hidden_layers, dc.num_hidden_layers
-    tc1 = text_config(args.text); tc1.num_hidden_layers = 1
+    t_build = time.perf_counter()
+    with torch.device("meta"):
+        lm = Qwen3ForCausalLM(tc)
+    lm = lm.to_empty(device="cpu").eval()
+    _fast_init_(lm)
+    lm.model.rotary_emb = type(lm.model.rotary_emb)(config=tc)                # buffers (inv_freq) do not survive the meta device
     dc1 = dna_config(args.dna); dc1.num_hidden_layers = 1
-    torch.manual_seed(0)
     with torch.no_grad():
-        lm = Qwen3ForCausalLM(tc1).eval()
         enc = build_dna_model(dc1, seed=0)
-    layer, head, emb = lm.model.layers[0], lm.lm_head, lm.model.embed_tokens
+    t_build = time.perf_counter() - t_build
+    layer, head = lm.model.layers[0], lm.lm_head
 
-    def t(fn, reps=1):
-        fn()
+    def t(fn, reps=1, warm=True):
+        if warm:
+            fn()
         t0 = time.perf_counter()
         for _ in range(reps):
             fn()
         return (time.perf_counter() - t0) / reps
-    x = torch.randn(1, L, tc.hidden_size)
-    pos = torch.arange(L)[None]
-    rot = lm.model.rotary_emb(x, pos)
+
+    ids = torch.randint(0, tc.vocab_size - 8, (1, L))
     with torch.no_grad():
+        # ---- measured, full depth: one row of the ref-logps pass (grpo_trainer.py:510-520: all-position logits, log_softmax, gather)
+        def ref_row():
+            logits = lm(input_ids=ids).logits[:, :-1]
+            return torch.gather(logits[0].log_softmax(-1), 1, ids[0, 1:, None])
+        fwd_row_full = t(ref_row, warm=False)
+        # ---- measured, full depth: cached decode steps for the G rows at context P + C/2 (cache pre-filled, 8 real steps)
+        ctx = P + C // 2
+        cache = DynamicCache(config=tc)
+        kv = torch.randn(G, tc.num_key_value_heads, ctx, tc.head_dim) * 0.1
+        for li in range(nl):
+            cache.update(kv, kv, li)
+        nxt = torch.randint(0, tc.vocab_size - 8, (G, 1))
+        n_dec = 8
+        t0 = time.perf_counter()
+        for s_ in range(n_dec):
+            pos = torch.full((G, 1), ctx + s_, dtype=torch.long)
+            out = lm(input_ids=nxt, past_key_values=cache, position_ids=pos, use_cache=True)
+            nxt = out.logits[:, -1].argmax(-1, keepdim=True)
+        dec_step_full = (time.perf_counter() - t0) / n_dec
+        del cache, kv
+        # ---- measured on one layer (scaled by depth): forward at L and at P, encoder layer
+        x = torch.randn(1, L, tc.hidden_size)
+        pos = torch.arange(L)[None]
+        rot = lm.model.rotary_emb(x, pos)
         fwd_layer = t(lambda: layer(x, position_embeddings=rot, attention_mask=None, position_ids=pos))
-        fwd_layer_P = fwd_layer * (P / L)
         hC = torch.randn(1, L, tc.hidden_size)
         fwd_head = t(lambda: head(hC).float().log_softmax(-1))
-        dna_ids = torch.randint(4, dc.vocab_size, (2, args.dna_len))
         enc_fwd1 = t(lambda: enc.esm.encoder.layer[0](torch.randn(2, args.dna_len, dc.hidden_size)))
-        # one cached decode step of one layer at context ~P + C/2, B = G rows
-        from transformers import DynamicCache
-        ctx = P + C // 2
-        cache = DynamicCache(config=tc1)
-        kx = torch.randn(G, ctx, tc.hidden_size)
-        layer(kx, position_embeddings=lm.model.rotary_emb(kx, torch.arange(ctx)[None]), past_key_values=cache, position_ids=torch.arange(ctx)[None])
-        x1 = torch.randn(G, 1, tc.hidden_size); p1 = torch.tensor([[ctx]])
-        rot1 = lm.model.rotary_emb(x1, p1)
-        def dec():
-            layer(x1, position_embeddings=rot1, past_key_values=cache, position_ids=p1)
-            for l in cache.layers:                                         # keep the context length fixed between reps
-                if getattr(l, "keys", None) is not None:
-                    l.keys, l.values = l.keys[:, :, :ctx], l.values[:, :, :ctx]
-        dec_layer = t(dec, reps=3)
-        dec_head = t(lambda: head(torch.randn(G, 1, tc.hidden_size)), reps=2)
     xg = x.clone().requires_grad_(True)
+    for p_ in layer.parameters():
+        p_.requires_grad_(False)
+
     def fb():
         out = layer(xg, position_embeddings=rot, attention_mask=None, position_ids=pos)
         (out[0] if isinstance(out, tuple) else out).sum().backward()
     fwdbwd_layer = t(fb)
-    spent = 0.0
+    fwd_composed = nl * fwd_layer + fwd_head
     # compose the reference's schedule (per prompt group of G rows on one device)
     encode = nle * enc_fwd1                                               # 2 sequences of one row
-    t_rollout = G * encode + G * nl * fwd_layer_P + (C) * (nl * dec_layer + dec_head)
-    t_ref = G * (encode + nl * fwd_layer + fwd_head)
+    prefill_row = fwd_row_full * (P / L)                                  # the rollout's prompt pass (HF computes all-position logits there too)
+    t_rollout = G * (encode + prefill_row) + C * dec_step_full
+    t_ref = G * (encode + fwd_row_full)
     t_policy = G * (encode + nl * fwdbwd_layer + 3 * fwd_head)
     total = (t_rollout + t_ref + t_policy) * args.prompts_per_gpu
     toks = G * C * args.prompts_per_gpu
     return {"value": round(toks / total, 4), "unit": "tokens/s", "cores": cores, "kind": "port",
-            "sample": "oracle (HF Qwen3/ESM fp32) timed at real widths on 1 row x 1 decoder layer (fwd %.2fs, fwd+bwd %.2fs at L=%d), "
-                      "1 encoder layer (%.3fs), 1 cached decode layer step for G=%d rows (%.4fs), lm_head (%.2fs); composed with the "
-                      "reference's own schedule (G-fold re-encode/re-prefill, 3 passes): est. %.0f s per GRPO step"
-                      % (fwd_layer, fwdbwd_layer, L, enc_fwd1, G, dec_layer, fwd_head, total),
+            "sample": "oracle (HF Qwen3/ESM fp32, real widths). MEASURED at full depth (%d layers): 1 row of the ref-logps pass at L=%d incl. [L,V] "
+                      "logits (%.1fs), %d cached decode steps for G=%d rows at ctx %d (%.3fs/step); measured on 1 layer and scaled: fwd+bwd "
+                      "(%.2fs/layer), encoder layer (%.3fs); composed with the reference's own schedule (G-fold re-encode/re-prefill, 3 passes): "
+                      "est. %.0f s per GRPO step" % (nl, L, fwd_row_full, n_dec, G, ctx, dec_step_full, fwdbwd_layer, enc_fwd1, total),
+            "measured": {"fwd_row_full_depth_s": round(fwd_row_full, 2), "decode_step_full_depth_s": round(dec_step_full, 4),
+                         "fwd_layer_s": round(fwd_layer, 3), "fwdbwd_layer_s": round(fwdbwd_layer, 3), "lm_head_logsoftmax_s": round(fwd_head, 2),
+                         "encoder_layer_s": round(enc_fwd1, 4), "fwd_measured_over_composed": round(fwd_row_full / fwd_composed, 3),
+                         "model_build_s": round(t_build, 1)},
             "est_step_s": round(total, 1)}
+
+
+def bench_config(args, world):
+    """The `config` object both arms print (same keys, same values: the driver compares them)."""
+    B = args.G * args.prompts_per_gpu
+    return {"workload": workload_string(args), "shapes": f"{args.dna}+{args.text}", "rows_per_gpu": B, "parallelism": f"dp{world}",
+            "l2": "weights (8 GB) and activations (>60 GB) exceed the 126 MB L2 every step; no flush needed",
+            "weights": "seeded random init (no checkpoints offline)"}
 
 
 def run_reference(args):
@@ -385,17 +428,13 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.perf_counter()
-    vals = []
-    for _ in range(max(1, min(args.steps, 2))):                           # each "step" is one bounded-sample measurement
-        vals.append(cpu_reference(args))
-    cb = vals[-1]
-    v = sum(x["value"] for x in vals) / len(vals)
-    cb["value"] = round(v, 4)
+    cb = cpu_reference(args)                                              # one bounded-sample measurement (~1 min of host work)
     line = {"impl": "reference", "metric": "GRPO tokens/sec (rollout+update)", "value": cb["value"], "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(cb["est_step_s"] * 1e3, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_string(args), "how": "host cores via the CPU oracle: bounded sample at real widths, composed with the reference schedule",
-                       "shapes": f"{args.dna}+{args.text}", "parallelism": "cpu"},
+            "config": bench_config(args, max(1, args.gpus)),
+            "how": "host cores via the CPU oracle (one host, whatever --gpus says): bounded sample at real widths and depth, composed with the "
+                   "reference schedule; an EXTRAPOLATED estimate of a >20 min step, not a timed step",
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": round(time.perf_counter() - t0, 1)}
     print(json.dumps(line), flush=True)

@@ -164,7 +164,6 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
     uint8_t* sQ = smem;                          // 32 x D
     uint8_t* sK = smem + QROWS * D * 2;
     uint8_t* sV = sK + 2 * TILE;
-    __shared__ int s_last[64];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     STAMP(0);
@@ -415,68 +414,77 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
             if (t == 0) __stcg(p.part_lse + base, l > 0.f ? m * LN2 + logf(l) : -INFINITY);
         }
     }
-    __threadfence();
-    __syncthreads();
     STAMP(5);
     // ---- arrival counters: one per (row, kv head).  The private split-0 item of a (row, kv head) pair is its merger: it waits for
     //      the other n_slots - 1 partials and merges them, so the 64 merges of a step run on 64 different CTAs in parallel
     //      (a "last arriver merges" scheme serialises all 8 rows of a group on one late shared item).  All items of a launch are
     //      co-resident (checked on the host), so the bounded spin cannot deadlock.
+    //      A row's GQ query vectors live in ONE warp (16 % GQ == 0), so a warp publishes its rows by itself: stores, __syncwarp, one
+    //      release-reduction per row -- no CTA barrier, no fence, no returning atomic on the way out.
     const bool merger = !shared_pass && split == 0;
     if (!merger) {
-        if (tid < rows_per_unit && row_base + tid < p.R) atomicAdd(p.counters + (row_base + tid) * p.Hkv + kvh, 1);
+        __syncwarp();
+        if (warp_live) {
+            const int rows_in_warp = 16 / p.GQ;                       // shared pass: rows warp*rows_in_warp ..; private pass: the one row
+            const int rr = shared_pass ? warp * rows_in_warp + lane : 0;
+            if (lane < (shared_pass ? rows_in_warp : 1) && rr < rows_per_unit && row_base + rr < p.R)
+                asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.counters + (row_base + rr) * p.Hkv + kvh) : "memory");
+        }
         STAMP(6); STAMP(7);
         return;
     }
+    __syncthreads();                                                   // the merger's own partial (warp 0) is complete
     if (tid == 0) {
-        const int* c = p.counters + row_base * p.Hkv + kvh;
+        int* c = p.counters + row_base * p.Hkv + kvh;
         int seen;
-        do {
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(c) : "memory");
-            if (seen < p.n_slots - 1) __nanosleep(40);
-        } while (seen < p.n_slots - 1);
+        do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(c) : "memory"); } while (seen < p.n_slots - 1);
+        *c = 0;                                                        // nobody touches it again before the next launch
     }
     __syncthreads();
-    s_last[0] = 1;                                                 // rows_per_unit == 1 here
-    __syncthreads();
-    // merge (all rows this CTA is the last arriver for, in one pass): thread (row, head) turns the n_slots LSEs into weights in
-    // shared memory; then every thread issues its independent 16-byte partial loads back to back (L2, fixed slot order).
-    float* s_w = reinterpret_cast<float*>(smem);                      // [rows_per_unit * GQ][n_slots] (tile smem is free now)
-    bool any = false;
-    for (int rr = 0; rr < rows_per_unit; ++rr) any |= (row_base + rr < p.R) && s_last[rr];
-    if (any) {
-        __threadfence();
-        for (int pair = tid; pair < rows_per_unit * p.GQ; pair += NT) {
-            const int rr = pair / p.GQ, hl = pair % p.GQ;
-            if (row_base + rr >= p.R || !s_last[rr]) continue;
-            const float* lse = p.part_lse + ((long long)(row_base + rr) * p.Hq + kvh * p.GQ + hl) * p.n_slots;
-            float mx = -INFINITY;
-            for (int s2 = 0; s2 < p.n_slots; ++s2) mx = fmaxf(mx, __ldcg(lse + s2));
-            float den = 0.f;
-            for (int s2 = 0; s2 < p.n_slots; ++s2) { const float l = __ldcg(lse + s2); den += (l == -INFINITY) ? 0.f : __expf(l - mx); }
-            const float inv = den > 0.f ? 1.f / den : 0.f;
-            for (int s2 = 0; s2 < p.n_slots; ++s2) { const float l = __ldcg(lse + s2); s_w[pair * p.n_slots + s2] = (l == -INFINITY) ? 0.f : __expf(l - mx) * inv; }
+    STAMP(6);
+    // merge of the n_slots partials of this (row, kv head): slot weights from the LSEs (one coalesced load per head, warp reductions),
+    // then every thread gathers its two float4 output chunks from all slots with up to 16 independent L2 loads in flight.
+    {
+        float* s_w = reinterpret_cast<float*>(smem);                   // [GQ][32] (tile smem is free now)
+        const int row = row_base;
+        for (int hl = warp; hl < p.GQ; hl += 2) {
+            const float* lse = p.part_lse + ((long long)row * p.Hq + kvh * p.GQ + hl) * p.n_slots;
+            const float l = lane < p.n_slots ? __ldcg(lse + lane) : -INFINITY;
+            const float mx = br::warp_max(l);
+            const float e = (l == -INFINITY) ? 0.f : __expf(l - mx);
+            const float den = br::warp_sum(e);
+            s_w[hl * 32 + lane] = den > 0.f ? e / den : 0.f;
         }
         __syncthreads();
         const int per_row = p.GQ * (D / 4);
-        for (int idx = tid; idx < rows_per_unit * per_row; idx += NT) {
-            const int rr = idx / per_row, rem = idx % per_row;
-            if (row_base + rr >= p.R || !s_last[rr]) continue;
-            const int hl = rem / (D / 4), d4 = (rem % (D / 4)) * 4;
-            const int row = row_base + rr, hq = kvh * p.GQ + hl;
-            const float* po = p.part_o + ((long long)row * p.Hq + hq) * p.n_slots * D + d4;
-            const float* wv = s_w + (rr * p.GQ + hl) * p.n_slots;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-            for (int s2 = 0; s2 < p.n_slots; ++s2) {
-                const float w = wv[s2];
-                const float4 v = __ldcg(reinterpret_cast<const float4*>(po + (long long)s2 * D));
-                acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+        for (int idx = tid; idx < per_row; idx += 2 * NT) {
+            const int idx2 = idx + NT;
+            const bool two = idx2 < per_row;
+            const int hlA = idx / (D / 4), dA = (idx % (D / 4)) * 4, hlB = two ? idx2 / (D / 4) : hlA, dB = two ? (idx2 % (D / 4)) * 4 : dA;
+            const float* poA = p.part_o + ((long long)row * p.Hq + kvh * p.GQ + hlA) * p.n_slots * D + dA;
+            const float* poB = p.part_o + ((long long)row * p.Hq + kvh * p.GQ + hlB) * p.n_slots * D + dB;
+            float4 accA = make_float4(0.f, 0.f, 0.f, 0.f), accB = accA;
+            for (int s0 = 0; s0 < p.n_slots; s0 += 8) {
+                float4 va[8], vb[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const bool ok = s0 + j < p.n_slots;
+                    va[j] = ok ? __ldcg(reinterpret_cast<const float4*>(poA + (long long)(s0 + j) * D)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    vb[j] = (ok && two) ? __ldcg(reinterpret_cast<const float4*>(poB + (long long)(s0 + j) * D)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {                          // fixed slot order: deterministic
+                    const float wa = (s0 + j < p.n_slots) ? s_w[hlA * 32 + s0 + j] : 0.f, wb = (s0 + j < p.n_slots) ? s_w[hlB * 32 + s0 + j] : 0.f;
+                    accA.x += wa * va[j].x; accA.y += wa * va[j].y; accA.z += wa * va[j].z; accA.w += wa * va[j].w;
+                    accB.x += wb * vb[j].x; accB.y += wb * vb[j].y; accB.z += wb * vb[j].z; accB.w += wb * vb[j].w;
+                }
             }
-            *reinterpret_cast<uint2*>(p.out + (long long)row * p.ldo + (long long)hq * D + d4) =
-                make_uint2(br::pack_bf16(acc.x, acc.y), br::pack_bf16(acc.z, acc.w));
+            *reinterpret_cast<uint2*>(p.out + (long long)row * p.ldo + (long long)(kvh * p.GQ + hlA) * D + dA) =
+                make_uint2(br::pack_bf16(accA.x, accA.y), br::pack_bf16(accA.z, accA.w));
+            if (two)
+                *reinterpret_cast<uint2*>(p.out + (long long)row * p.ldo + (long long)(kvh * p.GQ + hlB) * D + dB) =
+                    make_uint2(br::pack_bf16(accB.x, accB.y), br::pack_bf16(accB.z, accB.w));
         }
-        if (tid == 0) p.counters[row_base * p.Hkv + kvh] = 0;
     }
     STAMP(7);
 }

@@ -228,8 +228,8 @@ class RolloutEngine:
             St.cur_len = cur0.clone()
             St.uniforms = uniforms.clone() if params.do_sample else None
             St.scratch = ops.skinny_scratch(max(cfg.vocab_size, 2 * cfg.intermediate_size), dev)
-            splits_shared = min(8, n_shared) if n_shared > 0 else 0
-            splits_private = 2 if n_shared > 0 else 8
+            splits_shared = min(int(os.environ.get("BR_ATTN_SS", 8)), n_shared) if n_shared > 0 else 0
+            splits_private = int(os.environ.get("BR_ATTN_SP", 2)) if n_shared > 0 else 8
             cap = 3 * torch.cuda.get_device_properties(dev).multi_processor_count      # the fused kernel's merger items need co-residency
             n_items = lambda ss, sp: (R // G) * Hkv * ss + R * Hkv * sp
             while n_items(splits_shared, splits_private) > cap and (splits_shared > 1 or splits_private > 1):
