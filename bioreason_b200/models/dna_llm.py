@@ -197,6 +197,7 @@ class DNALLMModel(nn.Module):
                 gv.copy_(w[:F].view(F // 8, 8, -1)); uv.copy_(w[F:].view(F // 8, 8, -1))
         refresh_decoder_gu(self.text_model, self._dec)
         self._rollout_dec = None
+        self._enc_cache = None
         if getattr(self, "_rollout", None) is not None:
             self._rollout._cached.clear()
         self.sync_projection()
@@ -285,14 +286,48 @@ class DNALLMModel(nn.Module):
             dna_ids = dna_tokenized["input_ids"].to(dev)
             dna_mask = dna_tokenized["attention_mask"].to(dev)
             row_map, n_feat, n_slots = engine.dna_row_map(input_ids, self.dna_token_id, dna_mask, list(batch_idx_map))
-            n_feat, n_slots = torch.stack([n_feat, n_slots]).tolist()       # the one host sync (reference: n_seq + 1)
+            # GRPO batches repeat every prompt G times (RepeatRandomSampler): encode each distinct DNA sequence once.  dup[i] = sequence i
+            # equals sequence i - k (k sequences per batch item); the flags ride on the one host sync this call makes anyway.
+            n_seq = dna_ids.shape[0]
+            k = n_seq // B if B and n_seq % B == 0 and list(batch_idx_map) == [i // max(1, n_seq // B) for i in range(n_seq)] else 0
+            dup = torch.zeros(n_seq, dtype=torch.long, device=dev)
+            if k and n_seq > k:
+                dup[k:] = ((dna_ids[k:] == dna_ids[:-k]).all(dim=1) & (dna_mask[k:] == dna_mask[:-k]).all(dim=1)).long()
+            host = torch.cat([torch.stack([n_feat, n_slots]), dup]).tolist()  # the one host sync (reference: n_seq + 1)
+            n_feat, n_slots, dup = host[0], host[1], host[2:]
             if n_feat != n_slots:
                 raise ValueError(f"DNA features and DNA tokens do not match: features {n_feat}, tokens: {n_slots}")
-            with torch.no_grad():
-                enc = engine.encoder_forward(self._enc, dna_ids, dna_mask)  # [n_seq*S, d_dna], never gets grad
+            enc = self._encode_unique(dna_ids, dna_mask, dup, k)
             ops.gemm(enc, self._proj_w16, bias=self._proj_b16, out=emb, row_map=row_map)
             aux = (enc, row_map)
         return (emb, aux) if return_proj_inputs else emb
+
+    def _encode_unique(self, dna_ids, dna_mask, dup, k):
+        """Encoder output [n_seq * S, d_dna] with every distinct sequence encoded once; the result of the last call is kept and reused
+        while the same id tensors come back unmodified (the frozen encoder runs under no_grad in the reference too, dna_llm.py:121):
+        the reference-policy pass and the policy pass of one GRPO step share one encoder run."""
+        key = (dna_ids.data_ptr(), dna_ids._version, tuple(dna_ids.shape), dna_mask.data_ptr(), dna_mask._version)
+        cached = getattr(self, "_enc_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        n_seq, S = dna_ids.shape
+        src = list(range(n_seq))
+        for i in range(n_seq):
+            if dup[i]:
+                src[i] = src[i - k]
+        uniq = sorted(set(src))
+        with torch.no_grad():
+            if len(uniq) == n_seq:
+                enc = engine.encoder_forward(self._enc, dna_ids, dna_mask)
+            else:
+                ut = torch.tensor(uniq, device=dna_ids.device)
+                enc_u = engine.encoder_forward(self._enc, dna_ids[ut], dna_mask[ut])
+                slot = {u: j for j, u in enumerate(uniq)}
+                seq_slot = torch.tensor([slot[src[i]] for i in range(n_seq)], device=dna_ids.device, dtype=torch.int32)
+                rows = (seq_slot[:, None] * S + torch.arange(S, device=dna_ids.device, dtype=torch.int32)[None, :]).reshape(-1).contiguous()
+                enc = ops.gather_rows(enc_u, rows)
+        self._enc_cache = (key, enc, dna_ids, dna_mask)                     # the tensors are held so their storage cannot be recycled
+        return enc
 
     def process_dna_embeddings(self, dna_tokenized: Dict[str, torch.Tensor], batch_idx_map: List[int], batch_size: int) -> List[torch.Tensor]:
         """dna_llm.py:103-179 as a standalone call: encoder (no grad) -> projector -> the first `valid_length` rows of every

@@ -215,7 +215,10 @@ class DNALLMGRPOTrainer:
         pi = self._prepare_prompt_inputs(inputs)
         dev = model._dec.embed.device
         prompt_ids, prompt_mask = pi["input_ids"].to(dev), pi["attention_mask"].to(dev)
-        mm = dict(dna_tokenized=pi.get("dna_tokenized"), batch_idx_map=pi.get("batch_idx_map"))
+        dna = pi.get("dna_tokenized")
+        if dna is not None:                                                # device-resident once: the three passes of the step reuse the tensors
+            dna = {k: dna[k].to(dev) for k in ("input_ids", "attention_mask")}
+        mm = dict(dna_tokenized=dna, batch_idx_map=pi.get("batch_idx_map"))
         B, P = prompt_ids.shape
         C = self.max_completion_length
         if uniforms is None:

@@ -7,8 +7,10 @@
  *   - plain pointers + sizes, no torch types; every pointer is a CUDA device pointer unless noted;
  *   - every call enqueues on `stream` (a cudaStream_t) and returns without synchronising;
  *   - return 0 on success, <0 on error; `br_last_error()` gives the (thread-local) message;
- *   - the caller (PyTorch) owns all buffers; the library keeps no pointer past the call, except the
- *     NCCL communicator handle (`br_comm_*`);
+ *   - the caller (PyTorch) owns all buffers (including every workspace / scratch buffer named below); the library keeps no
+ *     pointer past the call.  There is no communicator handle: the two collectives of the path (reward all-gather, flat
+ *     gradient all-reduce) are issued by the host through torch.distributed / NCCL, not through this ABI;
+ *   - tensors are (pointer, leading dimension in elements) pairs, row-major; there is no tensor struct;
  *   - bf16 = __nv_bfloat16 storage, fp32 accumulation everywhere.
  * This file is parsed by cffi (ABI mode): keep it plain C, no macros beyond the constants below.
  */

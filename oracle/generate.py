@@ -14,7 +14,8 @@ from transformers.generation.logits_process import TemperatureLogitsWarper, TopK
 def manual_generate(oracle, batch, *, max_new_tokens, do_sample=False, temperature=1.0, top_k=50, top_p=1.0, uniforms=None,
                     eos_token_id=None, pad_token_id=0, return_margins=False):
     embeds = oracle._merged_embeds(batch["input_ids"], batch.get("dna_tokenized"), batch.get("batch_idx_map"))
-    mask = batch["attention_mask"].clone()
+    dev = embeds.device                                                     # the checker may run on the GPU (fp32) for the real-vocab tests
+    mask = batch["attention_mask"].clone().to(dev)
     B = embeds.shape[0]
     warpers = []
     if do_sample:
@@ -24,7 +25,7 @@ def manual_generate(oracle, batch, *, max_new_tokens, do_sample=False, temperatu
             warpers.append(TopKLogitsWarper(top_k=top_k, min_tokens_to_keep=1))
         if top_p < 1.0:
             warpers.append(TopPLogitsWarper(top_p=top_p, min_tokens_to_keep=1))
-    unfinished = torch.ones(B, dtype=torch.long)
+    unfinished = torch.ones(B, dtype=torch.long, device=dev)
     out, margins = [], []
     emb_table = oracle.text_model.get_input_embeddings()
     for step in range(max_new_tokens):
@@ -38,7 +39,7 @@ def manual_generate(oracle, batch, *, max_new_tokens, do_sample=False, temperatu
                 scores = w(None, scores)
             probs = torch.softmax(scores, dim=-1)
             cdf = probs.cumsum(-1)
-            u = uniforms[step].to(cdf.dtype)[:, None] * cdf[:, -1:]
+            u = uniforms[step].to(device=dev, dtype=cdf.dtype)[:, None] * cdf[:, -1:]
             nxt = (cdf > u).int().argmax(-1)
         else:
             nxt = logits.argmax(-1)
@@ -47,7 +48,7 @@ def manual_generate(oracle, batch, *, max_new_tokens, do_sample=False, temperatu
             unfinished = unfinished & (nxt != eos_token_id).long()
         out.append(nxt)
         embeds = torch.cat([embeds, emb_table(nxt)[:, None, :]], dim=1)
-        mask = torch.cat([mask, torch.ones(B, 1, dtype=mask.dtype)], dim=1)
+        mask = torch.cat([mask, torch.ones(B, 1, dtype=mask.dtype, device=dev)], dim=1)
         if eos_token_id is not None and unfinished.max() == 0:
             break
     ids = torch.stack(out, dim=1)

@@ -1,25 +1,56 @@
-"""A handful of representative launches for `ncu --set full`: the big decoder GEMMs (tensor-bound) and the decode weight
-streaming GEMMs (HBM-bound) at config (c) shapes."""
-import os, sys
+"""One representative launch of every hot kernel at config (c) shapes for `ncu --set full --profile-from-start off`:
+the big decoder GEMMs and the fused lm_head (tensor-bound), tcgen05 flash attention forward / backward, the LoRA-gradient TN GEMM,
+the decode weight-streaming GEMMs (HBM-bound) and the fused decode attention.  Everything is warmed up once outside the profiled range."""
+import math, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from bioreason_b200 import ops
 dev, bf = "cuda", torch.bfloat16
-M, d, F, NQ, V = 8 * 2360, 2560, 9728, 6144, 151936
+B, L, d, F, NQ, V, Hq, Hkv, D, r = 8, 2360, 2560, 9728, 6144, 151936, 32, 8, 128, 32
+M = B * L
 mk = lambda *s: (torch.randn(*s, device=dev) * 0.02).to(bf)
 x = mk(M, d); w_qkv = mk(NQ, d); w_gu = mk(2 * F, d); act = mk(M, F); w_down = mk(d, F); res = mk(M, d)
 emb = mk(V, d); h_sel = mk(4096, d); tgt = torch.randint(0, V, (4096,), device=dev)
-for _ in range(2):                                       # launches 0-7: warm-up + the ones ncu keeps (use -s 4 -c 4)
+qkv = mk(M, NQ) * 20; dout = mk(M, Hq * D); dqkv = torch.empty(M, NQ, device=dev, dtype=bf)
+t_qkv = mk(M, 3 * r); dgu = mk(M, 2 * F); t_gu = mk(M, 2 * r)
+g_q, g_k, g_v = (torch.zeros(n, r, device=dev) for n in (Hq * D, Hkv * D, Hkv * D))
+g_gate, g_up, g_a = torch.zeros(F, r, device=dev), torch.zeros(F, r, device=dev), torch.zeros(r, F, device=dev)
+u_down = mk(M, r)
+R, G, P, gen, PAGE = 8, 8, 1848, 256, 64
+xs = mk(R, d); xf = mk(R, F); xa = mk(R, Hq * D); scratch = ops.skinny_scratch(V, dev); ssq = torch.ones(80, 32, device=dev)
+T = P + gen; n_shared = P // PAGE; priv = math.ceil((T + 1 - n_shared * PAGE) / PAGE); max_pages = n_shared + priv
+table = torch.zeros(R, max_pages, dtype=torch.int32); nxt = n_shared
+for i in range(R):
+    table[i, :n_shared] = torch.arange(n_shared, dtype=torch.int32); table[i, n_shared:] = torch.arange(nxt, nxt + priv, dtype=torch.int32); nxt += priv
+table = table.to(dev)
+kc = torch.randn(nxt, Hkv, PAGE, D, device=dev).to(bf); vc = torch.randn_like(kc)
+qn = torch.ones(D, device=dev).to(bf); cur = torch.full((R,), T, dtype=torch.int32, device=dev)
+rope = ops.rope_table(T + 8, D, 1e6, dev); wsf = ops.decode_fused_workspace(R, Hq, Hkv, D, 10, dev)
+attn_out = torch.empty(R, Hq * D, device=dev, dtype=bf); q_dec = mk(R, NQ)
+
+
+def run():
     ops.gemm(x, w_qkv)                                   # [18880 x 2560] x [6144 x 2560]^T
     ops.gemm(x, w_gu, act=1)                             # gate/up with the fused SwiGLU epilogue
     ops.gemm(act, w_down, residual=res)                  # down_proj + residual
     ops.lmhead_logprob(h_sel, emb, tgt)                  # fused lm_head + LSE (logits never in HBM)
-torch.cuda.synchronize()
-R = 8
-xs = mk(R, d); scratch = ops.skinny_scratch(V, dev); ssq = torch.ones(80, 32, device=dev)
-for _ in range(2):                                       # skinny launches: lm_head, gate/up, qkv
+    q, k, v = qkv[:, :Hq * D], qkv[:, Hq * D:(Hq + Hkv) * D], qkv[:, (Hq + Hkv) * D:]
+    o, lse = ops.attn_fwd(q, k, v, B, L, Hq, Hkv, D, causal=True, want_lse=True)                 # tcgen05 flash attention forward
+    ops.attn_bwd(q, k, v, o, dout, lse, dqkv[:, :Hq * D], dqkv[:, Hq * D:(Hq + Hkv) * D], dqkv[:, (Hq + Hkv) * D:], B, L, Hq, Hkv, D)
+    ops.lora_grad_tn(dqkv, t_qkv, [(g_q, 0, Hq * D, 0, r), (g_k, Hq * D, (Hq + Hkv) * D, r, r), (g_v, (Hq + Hkv) * D, NQ, 2 * r, r)])
+    ops.lora_grad_tn(dgu, t_gu, [(g_gate, 0, 2 * F, 0, r), (g_up, 0, 2 * F, r, r)], mode=2)
+    ops.lora_grad_tn(act, u_down, [(g_a, 0, F, 0, r)], mode=1)
+    # decode: weight streaming + fused attention
     ops.skinny_gemm(xs, emb, scratch, mode=3, sumsq_in=ssq, sumsq_in_n=80, eps=1e-6)
-    ops.skinny_gemm(xs, w_gu, scratch, mode=2, sumsq_in=ssq, sumsq_in_n=80, eps=1e-6)
     ops.skinny_gemm(xs, w_qkv, scratch, sumsq_in=ssq, sumsq_in_n=80, eps=1e-6)
-torch.cuda.synchronize()
+    ops.skinny_gemm(xa, mk(d, Hq * D), scratch, mode=1, residual=xs)
+    ops.skinny_gemm(xs, w_gu, scratch, mode=2, sumsq_in=ssq, sumsq_in_n=80, eps=1e-6)
+    ops.skinny_gemm(xf, w_down, scratch, mode=1, residual=xs)
+    ops.decode_attn_fused(q_dec, qn, qn, kc, vc, table, cur, G, Hq, Hkv, D, n_shared, 8, 2, 1e6, 1e-6, wsf, attn_out, rope=rope)
+
+
+run(); torch.cuda.synchronize()
+torch.cuda.profiler.start()
+run(); torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("done")

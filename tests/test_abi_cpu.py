@@ -45,10 +45,17 @@ def test_sass_is_blackwell_native(built_lib):
     cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
     if not os.path.exists(cuobjdump):
         pytest.skip("cuobjdump not available")
-    obj = os.path.join(os.path.dirname(built_lib), "gemm_tc5.o")
-    sass = subprocess.run([cuobjdump, "-sass", obj], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
-        assert mnemonic in sass, mnemonic
+    # every contraction of the path -- GEMMs, decode weight streaming, flash attention forward / backward, LoRA gradients -- must be
+    # tcgen05 (UTCHMMA) fed by TMA (UTMALDG) with TMEM accumulators (LDTM), and must NOT contain the legacy mma.sync path (HMMA)
+    for name in ("gemm_tc5.o", "decode_gemm_tc5.o", "attn_fwd_tc5.o", "attn_bwd_tc5.o", "lora_grad_tc5.o"):
+        sass = subprocess.run([cuobjdump, "-sass", os.path.join(os.path.dirname(built_lib), name)], capture_output=True, text=True).stdout
+        for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+            assert mnemonic in sass, (name, mnemonic)
+        assert "HMMA." not in sass.replace("UTCHMMA", ""), f"{name} still contains mma.sync (HMMA)"
+    # P / dS / P^T operands are written to tensor memory by the softmax threads (tcgen05.st)
+    for name in ("attn_fwd_tc5.o", "attn_bwd_tc5.o"):
+        sass = subprocess.run([cuobjdump, "-sass", os.path.join(os.path.dirname(built_lib), name)], capture_output=True, text=True).stdout
+        assert "STTM" in sass, name
 
 
 def test_product_never_imports_the_oracle():
