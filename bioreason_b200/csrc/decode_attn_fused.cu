@@ -47,35 +47,6 @@ __global__ void rope_table_kernel(float2* __restrict__ out, int n_pos, int half,
     out[i] = make_float2(rbf(cs), rbf(sn));
 }
 
-// norm + rope of one 128-wide head vector held as (lo[2], hi[2]) per lane; returns roped values
-template <int D>
-__device__ __forceinline__ void norm_rope_words(uint32_t wlo, uint32_t whi, const bf16* __restrict__ w, int pos, float theta, float eps, int lane,
-                                                float (&olo)[D / 64], float (&ohi)[D / 64], const float2* __restrict__ rope, int rope_n_pos) {
-    constexpr int E = D / 64;
-    static_assert(E == 2, "head_dim 128");
-    const float2 a2 = br::unpack_bf16(wlo), b2 = br::unpack_bf16(whi);
-    const float lo[E] = {a2.x, a2.y}, hi[E] = {b2.x, b2.y};
-    const float ss = a2.x * a2.x + a2.y * a2.y + b2.x * b2.x + b2.y * b2.y;
-    const float rstd = rsqrtf(br::warp_sum(ss) / (float)D + eps);
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const int j = lane * E + e;
-        const float a = rbf(__bfloat162float(w[j]) * rbf(lo[e] * rstd));
-        const float b = rbf(__bfloat162float(w[D / 2 + j]) * rbf(hi[e] * rstd));
-        float sn, cs;
-        if (rope && pos < rope_n_pos) {                       // table built once per rollout by br_rope_table (same arithmetic)
-            const float2 t = __ldg(rope + (long long)pos * (D / 2) + j);
-            cs = t.x; sn = t.y;
-        } else {
-            const float inv_freq = 1.0f / powf(theta, (float)(2 * j) / (float)D);
-            sincosf((float)pos * inv_freq, &sn, &cs);
-            sn = rbf(sn); cs = rbf(cs);
-        }
-        olo[e] = rbf(a * cs) + rbf(-b * sn);
-        ohi[e] = rbf(b * cs) + rbf(a * sn);
-    }
-}
-
 // same arithmetic with the norm weights and the (cos, sin) pairs already in registers
 template <int D>
 __device__ __forceinline__ void norm_rope_words_pre(uint32_t wlo, uint32_t whi, const float (&wl)[D / 64], const float (&wh)[D / 64],
@@ -94,39 +65,8 @@ __device__ __forceinline__ void norm_rope_words_pre(uint32_t wlo, uint32_t whi, 
     }
 }
 
-// Quarter-warp version: 8 lanes own one 128-wide head vector (lane `sub` holds dims [8 sub, 8 sub + 8) of each half), so a warp
-// ropes 4 query vectors at once.  in/out: lo[8], hi[8] fp32.
-template <int D>
-__device__ __forceinline__ void norm_rope_q8(float (&lo)[8], float (&hi)[8], const bf16* __restrict__ w, int pos, int sub, float theta, float eps,
-                                             const float2* __restrict__ rope, int rope_n_pos) {
-    static_assert(D == 128, "head_dim 128");
-    float ss = 0.f;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) ss += lo[e] * lo[e] + hi[e] * hi[e];
-    ss += __shfl_xor_sync(0xffffffffu, ss, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-    const float rstd = rsqrtf(ss / (float)D + eps);
-    const uint4 wl = __ldg(reinterpret_cast<const uint4*>(w + sub * 8)), wh = __ldg(reinterpret_cast<const uint4*>(w + 64 + sub * 8));
-    const uint32_t wls[4] = {wl.x, wl.y, wl.z, wl.w}, whs[4] = {wh.x, wh.y, wh.z, wh.w};
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int j = sub * 8 + e;
-        const float2 wa = br::unpack_bf16(wls[e >> 1]), wb = br::unpack_bf16(whs[e >> 1]);
-        const float a = rbf(((e & 1) ? wa.y : wa.x) * rbf(lo[e] * rstd));
-        const float b = rbf(((e & 1) ? wb.y : wb.x) * rbf(hi[e] * rstd));
-        float sn, cs;
-        if (rope && pos < rope_n_pos) {
-            const float2 t = __ldg(rope + (long long)pos * (D / 2) + j);
-            cs = t.x; sn = t.y;
-        } else {
-            const float inv_freq = 1.0f / powf(theta, (float)(2 * j) / (float)D);
-            sincosf((float)pos * inv_freq, &sn, &cs);
-            sn = rbf(sn); cs = rbf(cs);
-        }
-        lo[e] = rbf(a * cs) + rbf(-b * sn);
-        hi[e] = rbf(b * cs) + rbf(a * sn);
-    }
-}
-// same arithmetic with the cos/sin pairs and the norm weights already in registers (all loads hoisted by the caller)
+// Quarter-warp layout: 8 lanes own one 128-wide head vector (lane `sub` holds dims [8 sub, 8 sub + 8) of each half), so a warp ropes 4 query
+// vectors at once; same arithmetic with the cos/sin pairs and the norm weights already in registers (all loads hoisted by the caller)
 template <int D>
 __device__ __forceinline__ void norm_rope_q8_pre(float (&lo)[8], float (&hi)[8], const float (&wl)[8], const float (&wh)[8], const float2 (&cs_sn)[8],
                                                  float eps) {
@@ -209,7 +149,10 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
     if (early1) issue_tile(1, pg1);
     cp_async_commit();
 
-    // query-prep operands that do not depend on the new tokens: positions, norm weights, rope pairs
+    // query-prep operands that do not depend on the new tokens: positions, norm weights, the rope pairs of the first pass.
+    // NOTE on code size: this prologue runs once per CTA, so every instruction is a cold instruction-cache fetch; the 4 passes are a
+    // real loop (one copy of the arithmetic, the next pass's rope pairs in flight) and there is no inline powf/sincosf fallback -- the
+    // host always supplies the rope table (the fully unrolled version was ~10 k instructions and cost ~3 us of fetch stalls per launch).
     const int q4 = lane >> 3, sub = lane & 7;
     int posv[4];
 #pragma unroll
@@ -217,40 +160,32 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
         const int s = warp * 16 + i * 4 + q4;
         const int rr = s / p.GQ;
         const bool ok = rr < rows_per_unit && (row_base + rr) < p.R;
-        posv[i] = ok ? __ldcg(p.cur_len + row_base + rr) : -1;
+        posv[i] = ok ? min(__ldcg(p.cur_len + row_base + rr), p.rope_n_pos - 1) : -1;
     }
     float wl[8], wh[8];
     { uint4 a = __ldg(reinterpret_cast<const uint4*>(p.qw + sub * 8)), b = __ldg(reinterpret_cast<const uint4*>(p.qw + 64 + sub * 8)); unpack8(a, wl); unpack8(b, wh); }
-    bool table_ok = p.rope != nullptr;
+    auto load_pairs = [&](int pos, float2 (&t)[8]) {
+        const float4* tp = reinterpret_cast<const float4*>(p.rope + (long long)(pos < 0 ? 0 : pos) * (D / 2) + sub * 8);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) table_ok &= (posv[i] < p.rope_n_pos);
-    table_ok = __all_sync(0xffffffffu, table_ok);               // warp-uniform: the shuffles below use the full mask
-    float2 tcs[4][8];
-    if (table_ok) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float4* tp = reinterpret_cast<const float4*>(p.rope + (long long)(posv[i] < 0 ? 0 : posv[i]) * (D / 2) + sub * 8);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { const float4 t4 = __ldg(tp + e); tcs[i][2 * e] = make_float2(t4.x, t4.y); tcs[i][2 * e + 1] = make_float2(t4.z, t4.w); }
-        }
-    }
+        for (int e = 0; e < 4; ++e) { const float4 t4 = __ldg(tp + e); t[2 * e] = make_float2(t4.x, t4.y); t[2 * e + 1] = make_float2(t4.z, t4.w); }
+    };
+    float2 tcs[8];
+    load_pairs(posv[0], tcs);
     // new-token K: norm weight + rope pair of the lane's two dims (owner item, warp 0)
     float2 kcs[E]; float kwl[E], kwh[E];
-    const bool k_table = owns_newest && p.rope != nullptr && (kv_len - 1) < p.rope_n_pos;
     if (owns_newest && warp == 0) {
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int j = lane * E + e;
             kwl[e] = __bfloat162float(p.kw[j]); kwh[e] = __bfloat162float(p.kw[D / 2 + j]);
-            kcs[e] = k_table ? __ldg(p.rope + (long long)(kv_len - 1) * (D / 2) + j) : make_float2(0.f, 0.f);
+            kcs[e] = __ldg(p.rope + (long long)min(kv_len - 1, p.rope_n_pos - 1) * (D / 2) + j);
         }
     }
     br::grid_dep_wait();
     STAMP(1);
 
-    // ---- queries: norm + rope straight into the swizzled smem tile (slot s -> row s / GQ, head kvh*GQ + s % GQ)
+    // ---- everything that depends on this step's qkv GEMM is requested at once: the raw query chunks and the new token's K / V
     {
-        // 8 lanes per query vector, 4 vectors per warp per pass, 4 passes: all 16-byte L2 loads are issued before any is used
         uint4 rl[4], rh[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -263,43 +198,60 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
                 rh[i] = __ldcg(reinterpret_cast<const uint4*>(src + 64 + sub * 8));
             }
         }
+        uint32_t kwlo = 0, kwhi = 0; uint4 vraw = make_uint4(0, 0, 0, 0);
+        if (owns_newest) {
+            if (warp == 0) load_head_words(p.qkv + (long long)row_base * p.ld + (long long)(p.Hq + kvh) * D, lane, kwlo, kwhi);
+            else if (lane < D / 8) vraw = __ldcg(reinterpret_cast<const uint4*>(p.qkv + (long long)row_base * p.ld + (long long)(p.Hq + p.Hkv + kvh) * D) + lane);
+        }
         STAMP(8);
+        // raw chunks -> their final (swizzled) place in the Q tile; each lane re-reads only what it wrote
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int s = warp * 16 + i * 4 + q4;
+            *reinterpret_cast<uint4*>(tile_ptr<D>(sQ, s, sub)) = rl[i];
+            *reinterpret_cast<uint4*>(tile_ptr<D>(sQ, s, 8 + sub)) = rh[i];
+        }
+        // ---- queries: norm + rope in place (slot s -> row s / GQ, head kvh*GQ + s % GQ); 8 lanes per vector, 4 vectors per warp per pass
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+            const int s = warp * 16 + i * 4 + q4;
+            const int pos = i == 0 ? posv[0] : (i == 1 ? posv[1] : (i == 2 ? posv[2] : posv[3]));
+            const int pos_n = i == 0 ? posv[1] : (i == 1 ? posv[2] : posv[3]);
+            float2 nxt[8];
+            if (i < 3) load_pairs(pos_n, nxt);                         // next pass's rope pairs in flight during this pass
             float lo[8], hi[8];
-            unpack8(rl[i], lo); unpack8(rh[i], hi);
-            if (table_ok) norm_rope_q8_pre<D>(lo, hi, wl, wh, tcs[i], p.eps);
-            else norm_rope_q8<D>(lo, hi, p.qw, posv[i] < 0 ? 0 : posv[i], sub, p.theta, p.eps, p.rope, p.rope_n_pos);
-            if (posv[i] < 0) {
+            unpack8(*reinterpret_cast<const uint4*>(tile_ptr<D>(sQ, s, sub)), lo);
+            unpack8(*reinterpret_cast<const uint4*>(tile_ptr<D>(sQ, s, 8 + sub)), hi);
+            norm_rope_q8_pre<D>(lo, hi, wl, wh, tcs, p.eps);
+            if (pos < 0) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) lo[e] = hi[e] = 0.f;
             }
             *reinterpret_cast<uint4*>(tile_ptr<D>(sQ, s, sub)) = pack8(lo);
             *reinterpret_cast<uint4*>(tile_ptr<D>(sQ, s, 8 + sub)) = pack8(hi);
+            if (i < 3) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) tcs[e] = nxt[e];
+            }
         }
-    }
-    STAMP(9);
-    // ---- append the new token's K / V (private item that owns the newest page)
-    if (owns_newest) {
-        const int pos = kv_len - 1;
-        const int page = table[newest_pg], slot = pos & 63;
-        if (warp == 0) {
-            float olo[E], ohi[E];
-            uint32_t kwlo, kwhi;
-            load_head_words(p.qkv + (long long)row_base * p.ld + (long long)(p.Hq + kvh) * D, lane, kwlo, kwhi);
-            if (k_table) norm_rope_words_pre<D>(kwlo, kwhi, kwl, kwh, kcs, p.eps, olo, ohi);
-            else norm_rope_words<D>(kwlo, kwhi, p.kw, pos, p.theta, p.eps, lane, olo, ohi, p.rope, p.rope_n_pos);
-            bf16* dst = p.kcache + ((long long)page * p.Hkv + kvh) * 64 * D + (long long)slot * D;
-            const int j0 = lane * E;
-            *reinterpret_cast<uint32_t*>(dst + j0) = br::pack_bf16(olo[0], olo[1]);
-            *reinterpret_cast<uint32_t*>(dst + D / 2 + j0) = br::pack_bf16(ohi[0], ohi[1]);
-        } else {
-            const bf16* src = p.qkv + (long long)row_base * p.ld + (long long)(p.Hq + p.Hkv + kvh) * D;
-            bf16* dst = p.vcache + ((long long)page * p.Hkv + kvh) * 64 * D + (long long)slot * D;
-            if (lane < D / 8) reinterpret_cast<uint4*>(dst)[lane] = __ldcg(reinterpret_cast<const uint4*>(src) + lane);
+        STAMP(9);
+        // ---- append the new token's K / V (private item that owns the newest page)
+        if (owns_newest) {
+            const int pos = kv_len - 1;
+            const int page = table[newest_pg], slot = pos & 63;
+            if (warp == 0) {
+                float olo[E], ohi[E];
+                norm_rope_words_pre<D>(kwlo, kwhi, kwl, kwh, kcs, p.eps, olo, ohi);
+                bf16* dst = p.kcache + ((long long)page * p.Hkv + kvh) * 64 * D + (long long)slot * D;
+                const int j0 = lane * E;
+                *reinterpret_cast<uint32_t*>(dst + j0) = br::pack_bf16(olo[0], olo[1]);
+                *reinterpret_cast<uint32_t*>(dst + D / 2 + j0) = br::pack_bf16(ohi[0], ohi[1]);
+            } else {
+                bf16* dst = p.vcache + ((long long)page * p.Hkv + kvh) * 64 * D + (long long)slot * D;
+                if (lane < D / 8) reinterpret_cast<uint4*>(dst)[lane] = vraw;
+            }
+            __threadfence();
         }
-        __threadfence();
     }
     __syncthreads();
     STAMP(2);
@@ -519,6 +471,7 @@ int br_decode_attn_fused(const void* qkv_raw, int64_t ld, const void* q_norm_w, 
     const int GQ = n_q_heads / n_kv_heads;
     BR_CHECK_ARG(GQ <= 16 && 16 % GQ == 0 && G * GQ <= 32, "decode_attn_fused: G * Hq/Hkv = %d query vectors per kv head exceed 32", G * GQ);
     BR_CHECK_ARG(splits_private >= 1 && splits_shared >= 0 && splits_private + splits_shared <= 32 && q_norm_w && k_norm_w, "decode_attn_fused: bad arguments (<= 32 splits)");
+    BR_CHECK_ARG(rope_table && rope_n_pos > 0, "decode_attn_fused: the cos/sin table of br_rope_table (covering every position of the rollout) is required");
     constexpr int D = 128;
     FusedParams p;
     p.qkv = (const bf16*)qkv_raw; p.ld = ld; p.qw = (const bf16*)q_norm_w; p.kw = (const bf16*)k_norm_w;

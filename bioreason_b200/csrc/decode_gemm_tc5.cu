@@ -150,7 +150,15 @@ __device__ __forceinline__ void compute_row_rstd(const SkParams& p, int et, floa
 __device__ __forceinline__ long long gtime_sk() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define SKSTAMP(k) do { if (p.dbg && (threadIdx.x == 64)) p.dbg[((long long)p.dbg_slot * 160 + blockIdx.x) * 8 + (k)] = gtime_sk(); } while (0)
 
-template <int BNX>
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+}
+
+// BNX: UMMA N (rows of X the tensor core sees, zero-filled beyond R); RM: rows the epilogue code is generated for (R <= RM <= BNX).
+// The epilogue runs once per CTA per launch -- straight-line, instruction-fetch-bound code -- so the common R <= 8 decode batch gets its
+// own half-size instantiation.
+template <int BNX, int RM>
 __global__ void __launch_bounds__(NTHREADS, 1)
 skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const SkParams p) {
     using L = SL<BNX>;
@@ -258,28 +266,37 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             const bool whole = (u == tile * p.KB) && (seg_end == (tile + 1) * p.KB);
             const int f = tile * BM + lane_grp * 32 + lane;
             const int part_row = tile * 4 + lane_grp;
-            float res[BNX];
-            load_residual<BNX>(p, f, res);                        // in flight while the accumulator is still being produced
+            float res[RM];
+            load_residual<RM>(p, f, res);                        // in flight while the accumulator is still being produced
             br::mbar_wait(&tfull_bar[as], aph);
             if (u == u_lo) SKSTAMP(3);
             br::tc_fence_after();
             const uint32_t taddr = tmem_base + as * BNX + ((uint32_t)(lane_grp * 32) << 16);
-            float v[BNX];
-#pragma unroll
-            for (int c = 0; c < BNX; c += 16) {
-                uint32_t r[16];
+            float v[RM];
+            if constexpr (RM == 8) {
+                uint32_t r[8];
                 __syncwarp();
-                tmem_ld_32x16(taddr + c, r);
+                tmem_ld_32x8(taddr, r);
                 br::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[c + i] = __uint_as_float(r[i]);
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < RM; c += 16) {
+                    uint32_t r[16];
+                    __syncwarp();
+                    tmem_ld_32x16(taddr + c, r);
+                    br::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[c + i] = __uint_as_float(r[i]);
+                }
             }
             br::tc_fence_before();
             __syncwarp();
             if (lane == 0) br::mbar_arrive(&tempty_bar[as]);   // accumulator drained into registers
             if (++as == 2) { as = 0; aph ^= 1; }
             if (whole) {
-                apply_epilogue<BNX>(p, f, lane, v, res, s_rs, part_row);
+                apply_epilogue<RM>(p, f, lane, v, res, s_rs, part_row);
             } else {
                 // Deterministic stream-K exchange.  A tile that spans several CTAs is finished by the FIRST of them (lowest index):
                 // for that CTA the tile is the last segment of its chunk, so it has nothing else left to do, while every other
@@ -291,7 +308,7 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 if ((int)blockIdx.x != first_c) {
                     float* mine = p.scratch + ((long long)blockIdx.x * 2 * BNX) * BM + lane_grp * 32 + lane;   // slot 0: the CTA's first tile
 #pragma unroll
-                    for (int r = 0; r < BNX; ++r)
+                    for (int r = 0; r < RM; ++r)
                         if (r < p.R) __stcg(mine + r * BM, v[r]);
                     __syncwarp();
                     if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.counters + tile) : "memory");
@@ -307,7 +324,7 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     SKSTAMP(4);
                     for (int c0 = first_c + 1; c0 <= last_c; c0 += 8) {          // 8 contributors x 8 rows of loads in flight
 #pragma unroll
-                        for (int r0 = 0; r0 < BNX; r0 += 8) {
+                        for (int r0 = 0; r0 < RM; r0 += 8) {
                             if (r0 >= p.R) break;                                // warp-uniform
                             float t[8][8];
 #pragma unroll
@@ -323,7 +340,7 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                         }
                     }
                     SKSTAMP(5);
-                    apply_epilogue<BNX>(p, f, lane, v, res, s_rs, part_row);
+                    apply_epilogue<RM>(p, f, lane, v, res, s_rs, part_row);
                     SKSTAMP(6);
                 }
             }
@@ -339,10 +356,10 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     }
 }
 
-template <int BNX>
+template <int BNX, int RM>
 int launch(const CUtensorMap& tw, const CUtensorMap& tx, const SkParams& p, int grid, cudaStream_t st) {
     using L = SL<BNX>;
-    auto kern = skinny_tc5_kernel<BNX>;
+    auto kern = skinny_tc5_kernel<BNX, RM>;
     static bool done = false;
     if (!done) { BR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL)); done = true; }
     BR_CHECK_CUDA(br_launch_pdl(kern, dim3(grid), dim3(NTHREADS), (size_t)L::TOTAL, st, tw, tx, p));
@@ -626,7 +643,8 @@ int br_skinny_gemm_ex(const void* X, int64_t ldx, const void* W, int64_t ldw, vo
     if ((rc = br_make_tmap_2d_bf16(&tw, W, N, K, ldw, BM))) return rc;
     if ((rc = br_make_tmap_2d_bf16(&tx, X, R, K, ldx, BNX))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    return BNX == 16 ? launch<16>(tw, tx, p, grid, st) : launch<32>(tw, tx, p, grid, st);
+    if (R <= 8) return launch<16, 8>(tw, tx, p, grid, st);
+    return BNX == 16 ? launch<16, 16>(tw, tx, p, grid, st) : launch<32, 32>(tw, tx, p, grid, st);
 }
 
 

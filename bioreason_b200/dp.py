@@ -42,6 +42,45 @@ def allreduce_mean_(buffers: Iterable[torch.Tensor]) -> None:
         b.div_(ws)
 
 
+class OverlappedGradReduce:
+    """C2 overlapped with the backward (the reference's DeepSpeed config sets overlap_comm, ds_config_stage2.json:28-33): the flat LoRA
+    gradient buffer is laid out layer by layer, and the backward finishes layers from the last to the first, so each layer's slice is
+    all-reduced (async, on NCCL's stream) as soon as its kernels are enqueued -- it runs under the remaining backward.  `finish()`
+    waits for the outstanding slices, reduces whatever was not covered (the projector buffers) and divides by the world size.
+    Averaging order: every element is summed over ranks exactly once, then divided -- same result as one all-reduce of the buffer."""
+
+    def __init__(self, flat: torch.Tensor):
+        self.flat, self.works, self.covered = flat, [], []
+        self.rank, self.ws = world()
+
+    def reduce_slice(self, lo: int, hi: int):
+        if self.ws == 1 or hi <= lo:
+            return
+        self.works.append(dist.all_reduce(self.flat[lo:hi], async_op=True))
+        self.covered.append((lo, hi))
+
+    def finish(self, extra: Iterable[torch.Tensor] = ()):
+        if self.ws == 1:
+            return
+        # slices of the flat buffer nobody reduced yet (e.g. overlap disabled for this step)
+        pos = 0
+        for lo, hi in sorted(self.covered):
+            if lo > pos:
+                self.works.append(dist.all_reduce(self.flat[pos:lo], async_op=True))
+            pos = max(pos, hi)
+        if pos < self.flat.numel():
+            self.works.append(dist.all_reduce(self.flat[pos:], async_op=True))
+        extra = list(extra)
+        for b in extra:
+            self.works.append(dist.all_reduce(b, async_op=True))
+        for w in self.works:
+            w.wait()
+        self.flat.div_(self.ws)
+        for b in extra:
+            b.div_(self.ws)
+        self.works, self.covered = [], []
+
+
 def rank_batches(sampler_indices: List[int], per_device: int):
     """Contiguous per-rank slices of the globally repeated index stream (what accelerate's batch sharding yields for
     the reference's RepeatRandomSampler, grpo_trainer.py:883-897): yields this rank's index list per global batch."""

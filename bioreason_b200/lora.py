@@ -135,6 +135,12 @@ class LoraState:
         for p, g in zip(self.params, self.grad_views):
             p.grad = g
 
+    def layer_slice(self, layer: int):
+        """[lo, hi) of the flat gradient buffer holding every adapter gradient of one decoder layer (parameters are laid out layer by layer)."""
+        per = len(TARGETS) * 2
+        lo = sum(g.numel() for g in self.grad_views[:layer * per])
+        return lo, lo + sum(g.numel() for g in self.grad_views[layer * per:(layer + 1) * per])
+
     def grad_view(self, layer: int, name: str, which: str) -> torch.Tensor:
         idx = (layer * len(TARGETS) + TARGETS.index(name)) * 2 + (0 if which == "A" else 1)
         return self.grad_views[idx]

@@ -293,8 +293,14 @@ class DNALLMGRPOTrainer:
             self.timings["policy_fwd"] += time.perf_counter() - t0
             if backward:
                 t0 = time.perf_counter()
+                # the last chunk of the last accumulation micro-step completes the gradients: all-reduce each layer's slice as the
+                # backward leaves it (C2 overlapped with the remaining backward)
+                hook = None
+                if hi == B and self._step % ga == 0 and _world()[1] > 1 and getattr(model, "_lora", None) is not None:
+                    self._reducer = dp.OverlappedGradReduce(model._lora.flat_grad)
+                    hook = lambda li, _m=model: self._reducer.reduce_slice(*_m._lora.layer_slice(li))
                 with self._mark("policy_bwd"):
-                    training.policy_backward(model, ctx, dlp * (w / ga))
+                    training.policy_backward(model, ctx, dlp * (w / ga), on_layer_done=hook)
                 self.timings["policy_bwd"] += time.perf_counter() - t0
         # clip_ratio is a ratio of sums; with row chunks it is weighted by rows (exact when chunks have equal mask counts)
         if self.beta > 0:
@@ -316,7 +322,12 @@ class DNALLMGRPOTrainer:
         model = self.model
         t0 = time.perf_counter()
         with self._mark("grad_allreduce"):
-            dp.allreduce_mean_([model._lora.flat_grad, model._proj_grad_w, model._proj_grad_b])     # C2: sum then / world (DDP average)
+            red = getattr(self, "_reducer", None)
+            if red is not None:                                            # slices already in flight under the backward; wait + the rest
+                red.finish([model._proj_grad_w, model._proj_grad_b])
+                self._reducer = None
+            else:
+                dp.allreduce_mean_([model._lora.flat_grad, model._proj_grad_w, model._proj_grad_b])     # C2: sum then / world (DDP average)
         with self._mark("optimizer"):
             model.attach_grads()
             if self.args.max_grad_norm and self.args.max_grad_norm > 0:

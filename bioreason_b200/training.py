@@ -67,8 +67,10 @@ def policy_forward(model, input_ids, attention_mask, dna_tokenized, batch_idx_ma
 
 
 @torch.no_grad()
-def policy_backward(model, ctx: PolicyCtx, dlogp: torch.Tensor):
-    """Accumulates d(sum dlogp * logp) into the LoRA flat gradient buffer and the projector's .grad buffers."""
+def policy_backward(model, ctx: PolicyCtx, dlogp: torch.Tensor, on_layer_done=None):
+    """Accumulates d(sum dlogp * logp) into the LoRA flat gradient buffer and the projector's .grad buffers.
+    on_layer_done(layer_index): called right after the kernels producing that layer's adapter gradients were enqueued (the
+    trainer hangs the overlapped gradient all-reduce of that layer's slice on it)."""
     W = model._dec
     W.build_transposes()
     cfg = W.cfg
@@ -150,6 +152,8 @@ def policy_backward(model, ctx: PolicyCtx, dlogp: torch.Tensor):
         dh = ops.rmsnorm_bwd(S.h_in, Lw.ln1, S.rstd1, dxn1, dres=dh_mid)
         del dxn1, dh_mid
         ctx.saved[li] = None                                              # free this layer's activations
+        if on_layer_done is not None and lora is not None:
+            on_layer_done(li)
 
     # ---------------- projector: emb rows that came from DNA features
     if ctx.aux is not None and model.dna_projection.weight.requires_grad:

@@ -33,6 +33,12 @@ def _worker(rank, world, port, ret):
         g1 = torch.full((10,), float(rank + 1)); g2 = torch.arange(4.0) * (rank + 1)
         dp.allreduce_mean_([g1, g2])
         assert torch.allclose(g1, torch.full((10,), 1.5)) and torch.allclose(g2, torch.arange(4.0) * 1.5)
+        # overlapped C2: slices reduced out of order while "the backward" goes on + the uncovered remainder + extra buffers == one all-reduce
+        flat = torch.arange(40.0) * (rank + 1); extra = torch.ones(3) * (rank + 1)
+        red = dp.OverlappedGradReduce(flat)
+        red.reduce_slice(30, 40); red.reduce_slice(10, 20)
+        red.finish([extra])
+        assert torch.allclose(flat, torch.arange(40.0) * 1.5) and torch.allclose(extra, torch.full((3,), 1.5))
         # sampler: same seed on every rank, contiguous per-rank slices, consecutive G rows share a prompt index
         s = list(iter(RepeatRandomSampler(range(12), G, (per_dev * world) // G, 1, seed=3)))
         mine_idx = list(dp.rank_batches(s, per_dev))

@@ -108,10 +108,11 @@ def test_decode_attention_paged_prefix_shared(ops, U, G, Hq, Hkv, plen, gen):
         wsf = ops.decode_fused_workspace(R, Hq, Hkv, D, ss + sp, "cuda")
         out2 = torch.empty_like(out)
         rope = ops.rope_table(T + 2, D, 1e6, "cuda")
-        for it in range(3):                                                # repeated: arrival counters must self-reset; with/without table
-            ops.decode_attn_fused(raw_qkv, qn, kn, kc2, vc2, table, cur, G, Hq, Hkv, D, n_shared, ss, sp, 1e6, 1e-6, wsf, out2,
-                                  rope=rope if it else None)
+        for it in range(3):                                                # repeated: arrival counters must self-reset
+            ops.decode_attn_fused(raw_qkv, qn, kn, kc2, vc2, table, cur, G, Hq, Hkv, D, n_shared, ss, sp, 1e6, 1e-6, wsf, out2, rope=rope)
             torch.testing.assert_close(out2.float(), ref, rtol=2e-2, atol=2e-2)
+        with pytest.raises(RuntimeError, match="cos/sin table"):           # the table is part of the contract (no inline sincos fallback)
+            ops.decode_attn_fused(raw_qkv, qn, kn, kc2, vc2, table, cur, G, Hq, Hkv, D, n_shared, ss, sp, 1e6, 1e-6, wsf, out2, rope=None)
         assert torch.equal(kc2, kc) and torch.equal(vc2, vc)
 
 

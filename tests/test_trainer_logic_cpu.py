@@ -53,7 +53,7 @@ def test_compute_loss_row_chunks_match_full_batch(monkeypatch, micro_rows, beta,
 
     got_grad = torch.zeros(B, C)
 
-    def fake_backward(model, ctx, dlp):
+    def fake_backward(model, ctx, dlp, on_layer_done=None):
         got_grad[ctx.rows] += dlp
 
     monkeypatch.setattr(training, "policy_forward", fake_policy_forward)
