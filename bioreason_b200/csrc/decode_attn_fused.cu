@@ -32,8 +32,9 @@ struct FusedParams {
     bf16* out; long long ldo;
     float scale_log2, theta, eps;
     long long* dbg;                      // optional [items, 16] globaltimer stamps (profiling aid)
-    const float2* rope;                  // [n_pos, D/2] (cos, sin), bf16-rounded like HF's tables; may be null (computed inline)
+    const float2* rope;                  // [n_pos, D/2] (cos, sin), bf16-rounded like HF's tables
     int rope_n_pos;
+    br::L2Prefetch pf; int pf_on;        // L2 staging of a later GEMM's weights (see br_common.cuh)
 };
 
 // cos/sin table: rope[pos, j] = (bf16(cos(pos * theta^(-2j/D))), bf16(sin(...))) -- the transcendental work of the decode loop, done once
@@ -98,7 +99,7 @@ __device__ __forceinline__ void load_head_words(const bf16* src, int lane, uint3
 }
 
 template <int D>
-__global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p, const __grid_constant__ CUtensorMap tmP) {
     constexpr int BN = 64, TILE = 64 * D * 2, NT = 64, QROWS = 32, E = D / 64;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sQ = smem;                          // 32 x D
@@ -148,6 +149,8 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p) {
     if (early0) issue_tile(0, pg_lo);
     if (early1) issue_tile(1, pg1);
     cp_async_commit();
+    // this kernel moves ~17 MB per layer and spends most of its life waiting: its CTAs stage weight tiles of a later GEMM into L2
+    if (p.pf_on && tid == 0) br::l2_prefetch_issue(&tmP, p.pf, blockIdx.x, gridDim.x);
 
     // query-prep operands that do not depend on the new tokens: positions, norm weights, the rope pairs of the first pass.
     // NOTE on code size: this prologue runs once per CTA, so every instruction is a cold instruction-cache fetch; the 4 passes are a
@@ -466,6 +469,16 @@ int br_decode_attn_fused(const void* qkv_raw, int64_t ld, const void* q_norm_w, 
                          const int32_t* page_table, int max_pages, const int32_t* cur_len, int R, int G, int n_q_heads, int n_kv_heads,
                          int head_dim, int n_shared_pages, int splits_shared, int splits_private, float scale, float theta, float eps,
                          const float* rope_table, int rope_n_pos, void* workspace, void* out, int64_t ldo, void* stream) {
+    return br_decode_attn_fused_pf(qkv_raw, ld, q_norm_w, k_norm_w, kcache, vcache, page_table, max_pages, cur_len, R, G, n_q_heads, n_kv_heads,
+                                   head_dim, n_shared_pages, splits_shared, splits_private, scale, theta, eps, rope_table, rope_n_pos, workspace,
+                                   out, ldo, nullptr, stream);
+}
+
+int br_decode_attn_fused_pf(const void* qkv_raw, int64_t ld, const void* q_norm_w, const void* k_norm_w, void* kcache, void* vcache,
+                            const int32_t* page_table, int max_pages, const int32_t* cur_len, int R, int G, int n_q_heads, int n_kv_heads,
+                            int head_dim, int n_shared_pages, int splits_shared, int splits_private, float scale, float theta, float eps,
+                            const float* rope_table, int rope_n_pos, void* workspace, void* out, int64_t ldo, const br_l2_prefetch* prefetch,
+                            void* stream) {
     BR_CHECK_ARG(head_dim == 128, "decode_attn_fused: head_dim 128 only");
     BR_CHECK_ARG(R > 0 && G > 0 && R % G == 0 && G <= 64, "decode_attn_fused: R=%d must be a multiple of G=%d (<= 64)", R, G);
     const int GQ = n_q_heads / n_kv_heads;
@@ -491,7 +504,15 @@ int br_decode_attn_fused(const void* qkv_raw, int64_t ld, const void* q_norm_w, 
     if (!done) { BR_CHECK_CUDA(cudaFuncSetAttribute(decode_fused_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); done = true; }
     const int items = (use_shared ? (R / G) * n_kv_heads * p.SS : 0) + R * n_kv_heads * p.SP;
     BR_CHECK_ARG(items <= 3 * br_num_sms(), "decode_attn_fused: %d work items exceed the co-resident capacity (3 per SM) the in-kernel merge relies on", items);
-    BR_CHECK_CUDA(br_launch_pdl(decode_fused_kernel<D>, dim3(items), dim3(64), (size_t)SMEM, (cudaStream_t)stream, p));
+    CUtensorMap tp;
+    memset(&tp, 0, sizeof(tp));
+    p.pf_on = 0;
+    if (prefetch && prefetch->W && prefetch->unit_hi > prefetch->unit_lo) {
+        int rc = br_make_l2_prefetch(prefetch, &tp, &p.pf.KB, &p.pf.units, &p.pf.chunk, &p.pf.n_chunks, &p.pf.a, &p.pf.b);
+        if (rc) return rc;
+        p.pf_on = 1;
+    }
+    BR_CHECK_CUDA(br_launch_pdl(decode_fused_kernel<D>, dim3(items), dim3(64), (size_t)SMEM, (cudaStream_t)stream, p, tp));
     return BR_OK;
 }
 

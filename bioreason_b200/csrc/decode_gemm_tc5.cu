@@ -37,6 +37,7 @@ struct SkParams {
     // written, never accumulated with atomics, and summed in a fixed order by the consumer: the rollout is reproducible.
     const float* sumsq_in; int sumsq_in_n; float* sumsq_out; float eps;
     long long* dbg; int dbg_slot;       // optional %globaltimer stamps [slot][cta][8] (profiling aid)
+    br::L2Prefetch pf; int pf_on;       // L2 staging of a later GEMM's weights (see br_common.cuh)
     int w_evict_first;                  // weight tiles are read once per token step: mark them evict-first in L2 so the small
                                         // latency-critical buffers (activations, partial tiles, statistics, tables) stay resident
 };
@@ -160,7 +161,8 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
 // own half-size instantiation.
 template <int BNX, int RM>
 __global__ void __launch_bounds__(NTHREADS, 1)
-skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const SkParams p) {
+skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmP,
+                  const SkParams p) {
     using L = SL<BNX>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -208,6 +210,7 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 br::mbar_expect_tx(&full_bar[i], L::STAGE);
                 load_w(smem + i * L::STAGE, &full_bar[i], kb * BK, tile * BM);
             }
+            if (p.pf_on) br::l2_prefetch_issue(&tmP, p.pf, blockIdx.x, gridDim.x);     // a LATER GEMM's tiles -> L2 (HBM is otherwise idle here)
             br::grid_dep_wait();
             for (int i = 0; i < n_pre; ++i) {
                 const int u = u_lo + i, tile = u / p.KB, kb = u - tile * p.KB;
@@ -357,12 +360,12 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 }
 
 template <int BNX, int RM>
-int launch(const CUtensorMap& tw, const CUtensorMap& tx, const SkParams& p, int grid, cudaStream_t st) {
+int launch(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& tp, const SkParams& p, int grid, cudaStream_t st) {
     using L = SL<BNX>;
     auto kern = skinny_tc5_kernel<BNX, RM>;
     static bool done = false;
     if (!done) { BR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL)); done = true; }
-    BR_CHECK_CUDA(br_launch_pdl(kern, dim3(grid), dim3(NTHREADS), (size_t)L::TOTAL, st, tw, tx, p));
+    BR_CHECK_CUDA(br_launch_pdl(kern, dim3(grid), dim3(NTHREADS), (size_t)L::TOTAL, st, tw, tx, tp, p));
     return BR_OK;
 }
 
@@ -603,16 +606,23 @@ int launch_chain(const ChainParams& cp, int grid, cudaStream_t st) {
 static long long* g_sk_dbg = nullptr;
 static int g_sk_dbg_slot = 0;
 
+int br_make_l2_prefetch(const br_l2_prefetch* spec, CUtensorMap* tmap, int* KB, int* units, int* chunk, int* n_chunks, int* a, int* b) {
+    BR_CHECK_ARG(spec->N % 16 == 0 && spec->K % 8 == 0 && spec->ldw % 8 == 0 && spec->unit_lo >= 0, "l2_prefetch: bad weight shape");
+    const int tiles_n = (spec->N + BM - 1) / BM;
+    *KB = (spec->K + BK - 1) / BK; *units = tiles_n * *KB;
+    int grid = *units < br_num_sms() ? *units : br_num_sms();
+    *chunk = (*units + grid - 1) / grid;
+    *n_chunks = (*units + *chunk - 1) / *chunk;
+    *a = spec->unit_lo; *b = spec->unit_hi;
+    return br_make_tmap_2d_bf16(tmap, spec->W, spec->N, spec->K, spec->ldw, BM);
+}
+
 extern "C" {
 
 int64_t br_skinny_scratch_bytes(int max_N) {
     // partial tiles [n_sms, 2, 32, 128] fp32 | grid-barrier word (16 ints) | one arrival counter per 128-feature tile
     return (int64_t)br_num_sms() * 2 * 32 * BM * sizeof(float) + 16 * sizeof(int) + (int64_t)(max_N / BM + 2) * sizeof(int);
 }
-
-int br_skinny_gemm_ex(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
-                      const void* residual, int64_t ldr, void* scratch, const float* sumsq_in, int sumsq_in_n, float* sumsq_out, float eps,
-                      void* stream);
 
 int br_skinny_gemm(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
                    const void* residual, int64_t ldr, void* scratch, void* stream) {
@@ -622,6 +632,12 @@ int br_skinny_gemm(const void* X, int64_t ldx, const void* W, int64_t ldw, void*
 int br_skinny_gemm_ex(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
                       const void* residual, int64_t ldr, void* scratch, const float* sumsq_in, int sumsq_in_n, float* sumsq_out, float eps,
                       void* stream) {
+    return br_skinny_gemm_pf(X, ldx, W, ldw, out, ldo, R, N, K, mode, residual, ldr, scratch, sumsq_in, sumsq_in_n, sumsq_out, eps, nullptr, stream);
+}
+
+int br_skinny_gemm_pf(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
+                      const void* residual, int64_t ldr, void* scratch, const float* sumsq_in, int sumsq_in_n, float* sumsq_out, float eps,
+                      const br_l2_prefetch* prefetch, void* stream) {
     BR_CHECK_ARG(R >= 1 && R <= 32, "skinny_gemm: R=%d must be in [1, 32]", R);
     BR_CHECK_ARG(N % 16 == 0 && K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "skinny_gemm: N %% 16, K %% 8, ld %% 8 (N=%d K=%d)", N, K);
     BR_CHECK_ARG(mode >= 0 && mode <= 3 && !(mode == 1 && !residual), "skinny_gemm: bad mode %d", mode);
@@ -642,9 +658,15 @@ int br_skinny_gemm_ex(const void* X, int64_t ldx, const void* W, int64_t ldw, vo
     int rc;
     if ((rc = br_make_tmap_2d_bf16(&tw, W, N, K, ldw, BM))) return rc;
     if ((rc = br_make_tmap_2d_bf16(&tx, X, R, K, ldx, BNX))) return rc;
+    CUtensorMap tp = tw;
+    p.pf_on = 0;
+    if (prefetch && prefetch->W && prefetch->unit_hi > prefetch->unit_lo) {
+        if ((rc = br_make_l2_prefetch(prefetch, &tp, &p.pf.KB, &p.pf.units, &p.pf.chunk, &p.pf.n_chunks, &p.pf.a, &p.pf.b))) return rc;
+        p.pf_on = 1;
+    }
     cudaStream_t st = (cudaStream_t)stream;
-    if (R <= 8) return launch<16, 8>(tw, tx, p, grid, st);
-    return BNX == 16 ? launch<16, 16>(tw, tx, p, grid, st) : launch<32, 32>(tw, tx, p, grid, st);
+    if (R <= 8) return launch<16, 8>(tw, tx, tp, p, grid, st);
+    return BNX == 16 ? launch<16, 16>(tw, tx, tp, p, grid, st) : launch<32, 32>(tw, tx, tp, p, grid, st);
 }
 
 

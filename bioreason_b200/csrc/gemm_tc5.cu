@@ -38,6 +38,7 @@ struct GemmParams {
     float* pmax; float* psum; float* tgt_logit;   // [M, n_tiles_n], [M, n_tiles_n], [M]
     const float* lse; const float* gscale;        // [M]
     int n_tiles_m, n_tiles_n;
+    int group_m;             // m-blocks per raster group (see tile_coords)
 };
 
 template <int BN>
@@ -50,9 +51,11 @@ struct SmemLayout {
     static constexpr int TOTAL = TILE_BYTES + 256 + 1024;   // + barriers + alignment slack
 };
 
-__device__ __forceinline__ void tile_coords(int tile, int ntm, int ntn, int& mb, int& nb) {
-    // grouped rasterisation: 16 m-blocks x all n-blocks per group keeps a wave's A and B panels L2-resident
-    constexpr int GROUP_M = 16;
+__device__ __forceinline__ void tile_coords(int tile, int ntm, int ntn, int GROUP_M, int& mb, int& nb) {
+    // grouped rasterisation: GROUP_M m-blocks x all n-blocks per group.  The group's A panel (GROUP_M x 128 x K, sized by the host to
+    // ~40 MB) stays L2-resident while every B panel streams past it once, so B is re-read from DRAM once per GROUP (with the fixed
+    // GROUP_M = 16 of round 1 the [18880 x 2560] x [19456 x 2560]^T gate/up GEMM re-read B 9 times: 1.08 GB of DRAM reads for 196 MB
+    // of operands).
     int per_group = GROUP_M * ntn;
     int g = tile / per_group;
     int first_m = g * GROUP_M;
@@ -105,7 +108,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                int mb, nb; tile_coords(tile, p.n_tiles_m, p.n_tiles_n, mb, nb);
+                int mb, nb; tile_coords(tile, p.n_tiles_m, p.n_tiles_n, p.group_m, mb, nb);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     br::mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* sa = smem + s * L::STAGE_BYTES;
@@ -154,7 +157,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int lane_grp = warp & 3;                     // TMEM lane group this warp may access
         int as = 0; uint32_t aph = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            int mb, nb; tile_coords(tile, p.n_tiles_m, p.n_tiles_n, mb, nb);
+            int mb, nb; tile_coords(tile, p.n_tiles_m, p.n_tiles_n, p.group_m, mb, nb);
             br::mbar_wait(&tfull_bar[as], aph);
             br::tc_fence_after();
             const int row = mb * BM + lane_grp * 32 + lane;
@@ -386,6 +389,13 @@ int run_gemm(int mode, const void* A, int64_t lda, const void* B, int64_t ldb, i
     p.M = M; p.N = N; p.K = K; p.K2 = (A2 && B2) ? K2 : 0;
     p.n_tiles_m = (M + BM - 1) / BM;
     p.n_tiles_n = (N + BN - 1) / BN;
+    {   // A panel of one raster group ~ 40 MB of the 126 MB L2 (the concurrently streaming B panels and the outputs need the rest)
+        const long long a_block = (long long)BM * (K + p.K2) * 2;
+        long long g = (40ll << 20) / (a_block > 0 ? a_block : 1);
+        if (g < 8) g = 8;
+        if (g > p.n_tiles_m) g = p.n_tiles_m;
+        p.group_m = (int)g;
+    }
     CUtensorMap ta, tb, ta2, tb2;
     int rc;
     if ((rc = br_make_tmap_2d_bf16(&ta, A, M, K, lda, BM))) return rc;

@@ -185,7 +185,8 @@ class RolloutEngine:
         # Static buffers + the captured decode graph are cached per rollout shape: a training run replays the same graph every
         # step (no per-step capture, no graph-pool / allocator churn -- that churn showed up as multi-second host stalls).
         key = (B, G, tuple(plen), C, n_shared, max_pages, n_pages, params.do_sample, params.temperature, params.top_k, params.top_p,
-               params.eos_token_id, params.pad_token_id, id(Wd), bool(use_graph), os.environ.get("BR_DECODE_CHAIN", "0"))
+               params.eos_token_id, params.pad_token_id, id(Wd), bool(use_graph), os.environ.get("BR_DECODE_CHAIN", "0"), os.environ.get("BR_L2PF", "0"),
+               os.environ.get("BR_ATTN_SS", ""), os.environ.get("BR_ATTN_SP", ""))
         St = self._cached.get(key)
         hit = St is not None
         if not hit:
@@ -304,17 +305,33 @@ class RolloutEngine:
             sample(b_logits)
             ops.decode_advance(step, cur_len)
 
+        # L2 staging plan (BR_L2PF=<fraction>, 0 disables): each launch pulls weight tiles of a LATER GEMM into L2 while HBM would idle
+        # under this launch's dependency waits / reductions.  Of every chunk a consumer CTA streams, tiles [0, 6) arrive through its own
+        # PDL pre-wait ring; a fraction of the rest is staged by the launches before it.
+        pf_frac = float(os.environ.get("BR_L2PF", "0"))
+
+        def stage(w, lo_frac, hi_frac):
+            if pf_frac <= 0.0:
+                return None
+            ch = ops.skinny_chunk_units(w)
+            span = max(0, ch - 6) * pf_frac
+            return (w, 6 + int(span * lo_frac), 6 + int(span * hi_frac))
+
         def decode_step_5():
             # 5 launches per layer: qkv GEMM (folded ln1), fused attention, o_proj (+res, sum x^2), gate/up GEMM (folded ln2, SwiGLU),
             # down_proj (+res, sum x^2); RMSNorm never launches in the decode loop.
             ops.embed_gather_sumsq(next_ids, Wd.embed, h, ssq_e)
+            nl_ = len(Wd.layers)
             for li, Lw in enumerate(Wd.layers):
-                ops.skinny_gemm(h, Lw.w_qkv, scratch, out=b_qkv, sumsq_in=ssq_e if li == 0 else ssq_a, sumsq_in_n=1 if li == 0 else n_part, eps=eps)
+                nxt_w = Wd.layers[li + 1].w_qkv if li + 1 < nl_ else Wd.lm_head
+                ops.skinny_gemm(h, Lw.w_qkv, scratch, out=b_qkv, sumsq_in=ssq_e if li == 0 else ssq_a, sumsq_in_n=1 if li == 0 else n_part, eps=eps,
+                                prefetch=stage(Lw.w_o, 0.0, 1.0))
                 ops.decode_attn_fused(b_qkv, Lw.q_norm, Lw.k_norm, kc[li], vc[li], table, cur_len, G, Hq, Hkv, D, n_shared, splits_shared,
-                                      splits_private, theta, eps, ws, attn_out, rope=rope)
-                ops.skinny_gemm(attn_out, Lw.w_o, scratch, mode=1, residual=h, out=b_x2, sumsq_out=ssq_b)
-                ops.skinny_gemm(b_x2, Lw.w_gu, scratch, mode=2, out=b_act, sumsq_in=ssq_b, sumsq_in_n=n_part, eps=eps)
-                ops.skinny_gemm(b_act, Lw.w_down, scratch, mode=1, residual=b_x2, out=h, sumsq_out=ssq_a)
+                                      splits_private, theta, eps, ws, attn_out, rope=rope, prefetch=stage(Lw.w_gu, 0.0, 0.65))
+                ops.skinny_gemm(attn_out, Lw.w_o, scratch, mode=1, residual=h, out=b_x2, sumsq_out=ssq_b, prefetch=stage(Lw.w_gu, 0.65, 1.0))
+                ops.skinny_gemm(b_x2, Lw.w_gu, scratch, mode=2, out=b_act, sumsq_in=ssq_b, sumsq_in_n=n_part, eps=eps, prefetch=stage(Lw.w_down, 0.0, 1.0))
+                ops.skinny_gemm(b_act, Lw.w_down, scratch, mode=1, residual=b_x2, out=h, sumsq_out=ssq_a,
+                                prefetch=stage(nxt_w, 0.0, 1.0) if li + 1 < nl_ else (stage(nxt_w, 0.0, 0.1) if pf_frac > 0 else None))
             ops.skinny_gemm(h, Wd.lm_head, scratch, mode=3, out=b_logits, sumsq_in=ssq_a, sumsq_in_n=n_part, eps=eps)
             sample(b_logits)
             ops.decode_advance(step, cur_len)

@@ -239,8 +239,29 @@ def skinny_scratch(max_n: int, device) -> torch.Tensor:
     return torch.zeros(lib().br_skinny_scratch_bytes(max_n), device=device, dtype=torch.uint8)
 
 
-def skinny_gemm(x, w, scratch, *, mode=0, residual=None, out=None, sumsq_in=None, sumsq_in_n=1, sumsq_out=None, eps=0.0):
-    """out[R, N] = x[R, K] @ w[N, K].T for R <= 32 decode rows (optionally with the folded-RMSNorm statistics)."""
+def _l2_prefetch(spec):
+    """(W_later, unit_lo, unit_hi) -> br_l2_prefetch* (or NULL): stage units [lo, hi) of every stream-K chunk of a later decode GEMM into L2."""
+    if spec is None:
+        return ffi.NULL, None
+    w, lo, hi = spec
+    if hi <= lo:
+        return ffi.NULL, None
+    pf = ffi.new("br_l2_prefetch*")
+    pf.W = ptr(w); pf.ldw = _row_major_2d(w); pf.N = w.shape[0]; pf.K = w.shape[1]; pf.unit_lo = int(lo); pf.unit_hi = int(hi)
+    return pf, w
+
+
+def skinny_chunk_units(w) -> int:
+    """16 KB weight tiles one CTA of skinny_gemm streams for weight w [N, K] (the stream-K chunk; mirrors br_skinny_gemm_ex)."""
+    n_sms = torch.cuda.get_device_properties(w.device).multi_processor_count
+    units = ((w.shape[0] + 127) // 128) * ((w.shape[1] + 63) // 64)
+    grid = min(units, n_sms)
+    return (units + grid - 1) // grid
+
+
+def skinny_gemm(x, w, scratch, *, mode=0, residual=None, out=None, sumsq_in=None, sumsq_in_n=1, sumsq_out=None, eps=0.0, prefetch=None):
+    """out[R, N] = x[R, K] @ w[N, K].T for R <= 32 decode rows (optionally with the folded-RMSNorm statistics).
+    prefetch=(W_later, unit_lo, unit_hi): also stage tiles of a later GEMM of the chain into L2 (see br_l2_prefetch)."""
     _need_cuda(x, w)
     R, K = x.shape
     N = w.shape[0]
@@ -249,10 +270,11 @@ def skinny_gemm(x, w, scratch, *, mode=0, residual=None, out=None, sumsq_in=None
             out = torch.empty(R, N, device=x.device, dtype=torch.float32)
         else:
             out = torch.empty(R, N // 2 if mode == 2 else N, device=x.device, dtype=torch.bfloat16)
-    check(lib().br_skinny_gemm_ex(ptr(x), _row_major_2d(x), ptr(w), _row_major_2d(w), ptr(out), _row_major_2d(out), R, N, K, mode,
+    pf, _keep = _l2_prefetch(prefetch)
+    check(lib().br_skinny_gemm_pf(ptr(x), _row_major_2d(x), ptr(w), _row_major_2d(w), ptr(out), _row_major_2d(out), R, N, K, mode,
                                   ptr(residual), _row_major_2d(residual) if residual is not None else 0, ptr(scratch),
                                   ptr(sumsq_in, "float*"), int(sumsq_in_n) if sumsq_in is not None else 0, ptr(sumsq_out, "float*"),
-                                  float(eps), _stream()),
+                                  float(eps), pf, _stream()),
           "skinny_gemm")
     return out
 
@@ -327,15 +349,16 @@ def rope_table(n_pos, head_dim, theta, device):
 
 
 def decode_attn_fused(qkv_raw, q_norm_w, k_norm_w, kcache, vcache, page_table, cur_len, G, n_q, n_kv, head_dim, n_shared_pages,
-                      splits_shared, splits_private, theta, eps, workspace, out, scale=None, rope=None):
+                      splits_shared, splits_private, theta, eps, workspace, out, scale=None, rope=None, prefetch=None):
     R = qkv_raw.shape[0]
     if scale is None:
         scale = head_dim ** -0.5
-    check(lib().br_decode_attn_fused(ptr(qkv_raw), _row_major_2d(qkv_raw), ptr(q_norm_w), ptr(k_norm_w), ptr(kcache), ptr(vcache),
-                                     ptr(page_table, "int32_t*"), page_table.shape[1], ptr(cur_len, "int32_t*"), R, G, n_q, n_kv,
-                                     head_dim, n_shared_pages, splits_shared, splits_private, float(scale), float(theta), float(eps),
-                                     ptr(rope, "float*"), rope.shape[0] if rope is not None else 0,
-                                     ptr(workspace), ptr(out), _row_major_2d(out), _stream()), "decode_attn_fused")
+    pf, _keep = _l2_prefetch(prefetch)
+    check(lib().br_decode_attn_fused_pf(ptr(qkv_raw), _row_major_2d(qkv_raw), ptr(q_norm_w), ptr(k_norm_w), ptr(kcache), ptr(vcache),
+                                        ptr(page_table, "int32_t*"), page_table.shape[1], ptr(cur_len, "int32_t*"), R, G, n_q, n_kv,
+                                        head_dim, n_shared_pages, splits_shared, splits_private, float(scale), float(theta), float(eps),
+                                        ptr(rope, "float*"), rope.shape[0] if rope is not None else 0,
+                                        ptr(workspace), ptr(out), _row_major_2d(out), pf, _stream()), "decode_attn_fused")
     return out
 
 

@@ -136,6 +136,14 @@ int br_skinny_gemm(const void* X, int64_t ldx, const void* W, int64_t ldw, void*
 int br_skinny_gemm_ex(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
                       const void* residual, int64_t ldr, void* scratch, const float* sumsq_in, int sumsq_in_n, float* sumsq_out,
                       float eps, void* stream);
+/* L2 staging for the decode loop.  The decode step is a chain of small dependent kernels; while one of them waits on its predecessor or
+ * reduces partial tiles, HBM idles.  A launch can therefore pull weight tiles of a LATER GEMM of the chain into the 126 MB L2:
+ * `W [N, K]` is that GEMM's weight, and of every chunk its CTAs will stream (the stream-K decomposition of br_skinny_gemm_ex) the 16 KB
+ * tiles [unit_lo, unit_hi) are prefetched.  Weights are constant during a rollout, so this is safe at any point of the chain. */
+typedef struct br_l2_prefetch { const void* W; int64_t ldw; int32_t N, K; int32_t unit_lo, unit_hi; } br_l2_prefetch;
+int br_skinny_gemm_pf(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
+                      const void* residual, int64_t ldr, void* scratch, const float* sumsq_in, int sumsq_in_n, float* sumsq_out,
+                      float eps, const br_l2_prefetch* prefetch, void* stream);
 /* Up to 4 dependent decode GEMMs in ONE persistent launch (e.g. o_proj -> gate/up -> down_proj -> next layer's qkv):
  * phases are separated by a grid-wide barrier inside the kernel and the weight producer prefetches across it, so the
  * HBM stream does not stall at layer boundaries.  Same per-phase semantics as br_skinny_gemm_ex. */
@@ -194,6 +202,12 @@ int br_decode_attn_fused(const void* qkv_raw, int64_t ld, const void* q_norm_w, 
                          int n_kv_heads, int head_dim, int n_shared_pages, int splits_shared, int splits_private, float scale,
                          float theta, float eps, const float* rope_table, int rope_n_pos, void* workspace, void* out, int64_t ldo,
                          void* stream);
+/* same, plus L2 staging of a later GEMM's weight tiles from this (HBM-light) launch; see br_l2_prefetch */
+int br_decode_attn_fused_pf(const void* qkv_raw, int64_t ld, const void* q_norm_w, const void* k_norm_w, void* kcache, void* vcache,
+                            const int32_t* page_table, int max_pages, const int32_t* cur_len, int R, int G, int n_q_heads, int n_kv_heads,
+                            int head_dim, int n_shared_pages, int splits_shared, int splits_private, float scale, float theta, float eps,
+                            const float* rope_table, int rope_n_pos, void* workspace, void* out, int64_t ldo, const br_l2_prefetch* prefetch,
+                            void* stream);
 /* rope_table [n_pos, head_dim/2, 2] f32 = (cos, sin) rounded to bf16 precision (HF builds its tables in the model dtype);
  * optional input of br_decode_attn_fused: removes powf/sincosf from the decode loop. */
 /* profiling aid: per-item phase timestamps ([items, 16] int64, %globaltimer ns) for the next fused-attention launches */

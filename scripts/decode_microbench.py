@@ -120,23 +120,33 @@ n_part = ((d + 127) // 128) * 4
 ssa = torch.ones(n_part, 32, device=dev); ssb = torch.ones(n_part, 32, device=dev)
 wsf = ops.decode_fused_workspace(R, Hq, Hkv, D, 10, dev)
 attn_out = torch.empty(R, Hq * D, device=dev, dtype=bf)
-def chain():
-    x = x0
-    for w in ws_l:
-        q = ops.skinny_gemm(x, w["qkv"], scratch, sumsq_in=ssa, sumsq_in_n=n_part, eps=1e-6)
-        ops.decode_attn_fused(q, qn, kn, kc, vc, table, cur, G, Hq, Hkv, D, n_shared, 8, 2, 1e6, 1e-6, wsf, attn_out, rope=rope)
-        x2 = ops.skinny_gemm(attn_out, w["o"], scratch, mode=1, residual=x, sumsq_out=ssb)
-        a = ops.skinny_gemm(x2, w["gu"], scratch, mode=2, sumsq_in=ssb, sumsq_in_n=n_part, eps=1e-6)
-        x = ops.skinny_gemm(a, w["down"], scratch, mode=1, residual=x2, sumsq_out=ssa)
-us = timed_graph(chain) / NL
-print(f"layer chain (5 launches): {us:8.2f} us per layer  -> {36 * us / 1e3:.3f} ms per token (36 layers)   PDL={'off' if os.environ.get('BR_NO_PDL') else 'on'}")
+SS_, SP_ = int(os.environ.get("BR_ATTN_SS", 8)), int(os.environ.get("BR_ATTN_SP", 2))
+wsf = ops.decode_fused_workspace(R, Hq, Hkv, D, SS_ + SP_, dev)
+for frac in (0.0, 0.5, 1.0):
+    def stage(w, lo, hi):
+        if frac <= 0:
+            return None
+        span = max(0, ops.skinny_chunk_units(w) - 6) * frac
+        return (w, 6 + int(span * lo), 6 + int(span * hi))
+    def chain():
+        x = x0
+        for i, w in enumerate(ws_l):
+            wn = ws_l[(i + 1) % NL]["qkv"]
+            q = ops.skinny_gemm(x, w["qkv"], scratch, sumsq_in=ssa, sumsq_in_n=n_part, eps=1e-6, prefetch=stage(w["o"], 0, 1))
+            ops.decode_attn_fused(q, qn, kn, kc, vc, table, cur, G, Hq, Hkv, D, n_shared, SS_, SP_, 1e6, 1e-6, wsf, attn_out, rope=rope, prefetch=stage(w["gu"], 0, 0.65))
+            x2 = ops.skinny_gemm(attn_out, w["o"], scratch, mode=1, residual=x, sumsq_out=ssb, prefetch=stage(w["gu"], 0.65, 1))
+            a = ops.skinny_gemm(x2, w["gu"], scratch, mode=2, sumsq_in=ssb, sumsq_in_n=n_part, eps=1e-6, prefetch=stage(w["down"], 0, 1))
+            x = ops.skinny_gemm(a, w["down"], scratch, mode=1, residual=x2, sumsq_out=ssa, prefetch=stage(wn, 0, 1))
+    us = timed_graph(chain) / NL
+    print(f"layer chain (5 launches, splits {SS_},{SP_}, L2 staging {frac:.1f}): {us:8.2f} us per layer  -> {36 * us / 1e3:.3f} ms per token (36 layers)   PDL={'off' if os.environ.get('BR_NO_PDL') else 'on'}")
 
 # ---- the production layout: fused attention + ONE persistent chain kernel (o -> gate/up -> down -> next qkv) per layer
 b_qkv = torch.empty(R, (Hq + 2 * Hkv) * D, device=dev, dtype=bf); b_x2 = torch.empty(R, d, device=dev, dtype=bf)
 b_act = torch.empty(R, F, device=dev, dtype=bf); hbuf = x0.clone()
+wsf2 = ops.decode_fused_workspace(R, Hq, Hkv, D, 10, dev)
 def chain2():
     for i, w in enumerate(ws_l):
-        ops.decode_attn_fused(b_qkv, qn, kn, kc, vc, table, cur, G, Hq, Hkv, D, n_shared, 8, 2, 1e6, 1e-6, wsf, attn_out, rope=rope)
+        ops.decode_attn_fused(b_qkv, qn, kn, kc, vc, table, cur, G, Hq, Hkv, D, n_shared, 8, 2, 1e6, 1e-6, wsf2, attn_out, rope=rope)
         ops.skinny_chain([dict(x=attn_out, w=w["o"], out=b_x2, mode=1, residual=hbuf, sumsq_out=ssb),
                           dict(x=b_x2, w=w["gu"], out=b_act, mode=2, sumsq_in=ssb, sumsq_in_n=n_part),
                           dict(x=b_act, w=w["down"], out=hbuf, mode=1, residual=b_x2, sumsq_out=ssa),
