@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--completion", type=int, default=512)
     ap.add_argument("--micro-rows", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the secondary resident-row lines (16 / 32 rows per GPU)")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     return ap.parse_args()
 
@@ -105,8 +106,8 @@ def make_prompt_batch(tc, dc, args, seed):
 
 
 def workload_string(args):
-    return ("(c) NT-v2-500M + Qwen3-4B GRPO step: %d prompt x G=%d per GPU, P=%d (2x%d DNA + %d text), C=%d, EOS suppressed, "
-            "mu=1, beta=0.04, LoRA r=32 + projector, AdamW" % (args.prompts_per_gpu, args.G, args.text_len + 2 * args.dna_len,
+    return ("(c) NT-v2-500M + Qwen3-4B GRPO step: %d prompt x G=%d per GPU, P=%d (2x%d DNA + 4 delimiters + %d text), C=%d, EOS suppressed, "
+            "mu=1, beta=0.04, LoRA r=32 + projector, AdamW" % (args.prompts_per_gpu, args.G, args.text_len + 2 * (args.dna_len + 2),
                                                                args.dna_len, args.text_len, args.completion))
 
 
@@ -117,7 +118,7 @@ def algorithmic_work(tc, dc, args):
     body = nl * ((Hq + 2 * Hkv) * D * d + Hq * D * d + 3 * F * d)                  # matmul params / token
     head = V * d
     G, C = args.G, args.completion
-    P = args.text_len + 2 * args.dna_len
+    P = args.text_len + 2 * (args.dna_len + 2)
     L = P + C
     npg = args.prompts_per_gpu
     attn = lambda n: nl * 4 * Hq * D * n * n / 2
@@ -275,6 +276,34 @@ def run_b200(args):
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
             "step_ms": per_step, "mem_gb": {"max_allocated": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
                                             "max_reserved": round(torch.cuda.max_memory_reserved() / 2 ** 30, 1)}}
+    # ---- secondary lines: more prompt groups resident per GPU (NOT the benchmark configuration: BASELINE config (c) is one group of
+    #      G = 8; the decode weight stream is amortised over more rows).  Row-chunked forward/backward (micro_rows = 8) keeps the
+    #      activation footprint of the 8-row step.
+    if world == 1 and not args.no_sweep and args.prompts_per_gpu == 1:
+        import copy
+        sweep = []
+        del trainer
+        torch.cuda.empty_cache()
+        for ppg in (2, 4):
+            try:
+                a2 = copy.copy(args); a2.prompts_per_gpu = ppg
+                B2 = args.G * ppg
+                cfg2 = DNALLMGRPOConfig(num_generations=args.G, max_completion_length=args.completion, per_device_train_batch_size=B2,
+                                        suppress_eos=True, micro_rows=args.G, seed=1234)
+                tr2 = DNALLMGRPOTrainer(model, [synthetic_reward], cfg2)
+                hb = make_prompt_batch(tc, dc, a2, seed=1000 + rank)
+                res2 = dict(input_ids=hb["input_ids"].cuda(), attention_mask=hb["attention_mask"].cuda(),
+                            dna_tokenized={k: v.cuda() for k, v in hb["dna_tokenized"].items()}, batch_idx_map=hb["batch_idx_map"])
+                for _ in range(2):
+                    tr2.training_step(res2)
+                ms2 = timed(2, lambda: tr2.training_step(res2)) / 2
+                sweep.append({"rows_per_gpu": B2, "prompts_per_gpu": ppg, "micro_rows": args.G, "value": round(B2 * args.completion / (ms2 / 1e3), 1),
+                              "ms_per_step": round(ms2, 1)})
+                del tr2, res2
+                torch.cuda.empty_cache()
+            except Exception as e:                                        # a secondary line must never take the measurement down
+                sweep.append({"rows_per_gpu": args.G * ppg, "error": repr(e)[:160]})
+        line["secondary_resident_rows"] = sweep
     if rank == 0 and world == 1 and not args.no_cpu_baseline:              # the CPU baseline is timed at N=1 only
         try:
             line["cpu_baseline"] = cpu_reference(args, budget_s=args.cpu_budget_s)
@@ -333,7 +362,7 @@ def cpu_reference(args, budget_s=25.0):
     torch.set_num_threads(cores)
     del a_, b_
     G, C = args.G, args.completion
-    P = args.text_len + 2 * args.dna_len
+    P = args.text_len + 2 * (args.dna_len + 2)
     L = P + C
     nl, nle = tc.num_hidden_layers, dc.num_hidden_layers
     t_build = time.perf_counter()

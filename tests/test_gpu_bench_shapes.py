@@ -97,7 +97,7 @@ def _grad_report(m, oracle):
 
 
 def test_config_c_logps_grads_microrows_determinism():
-    """Config (c) geometry: 1 prompt x G = 8, P = 1848 (2 x 668 DNA + 512 text), C = 512, L = 2360, Qwen3-4B widths."""
+    """Config (c) geometry: 1 prompt x G = 8, P = 1852 (2 x 668 DNA tokens + 4 delimiters + 512 text), C = 512, L = 2364, Qwen3-4B widths."""
     from bioreason_b200 import training
     from oracle.models import synth_batch
     tc, dc = _cfgs("qwen3-4b")
@@ -105,7 +105,7 @@ def test_config_c_logps_grads_microrows_determinism():
     G, C = 8, 512
     batch = synth_batch(tc, dc, batch=G, n_seq=2, dna_len=668, text_len=512, seed=8, same_prompt=True)
     P = batch["input_ids"].shape[1]
-    assert P == 1848
+    assert P == 512 + 2 * (668 + 2)                                        # text + per DNA sequence: <|dna_start|> 668 x <|dna_pad|> <|dna_end|>
     comp = torch.randint(0, tc.eos_token_id, (G, C), generator=torch.Generator().manual_seed(9))
     ids = torch.cat([batch["input_ids"], comp], 1).cuda()
     cmask = torch.ones(G, C, dtype=torch.long); cmask[1, -37:] = 0; cmask[5, -200:] = 0          # post-EOS tails
@@ -158,7 +158,7 @@ def test_config_c_logps_grads_microrows_determinism():
 
 
 def test_config_c_rollout_prefix_sharing_greedy_and_eos():
-    """Greedy decode at V = 151 936 / d = 2560 with the G = 8 prefix-shared paged KV (28 shared pages at P = 1848): ids vs the oracle's
+    """Greedy decode at V = 151 936 / d = 2560 with the G = 8 prefix-shared paged KV (28 shared pages at P = 1852): ids vs the oracle's
     greedy loop (margin-aware), graph == eager, and an EOS-terminated rollout (EOS := the token the oracle emits at step 3)."""
     from bioreason_b200.models import DNALLMModel
     from oracle.generate import manual_generate
@@ -175,7 +175,7 @@ def test_config_c_rollout_prefix_sharing_greedy_and_eos():
     want, margins = want.cpu().expand(G, -1), margins.cpu().expand(G, -1)
     ids_e, st = m.generate(**batch, max_new_tokens=n, do_sample=False, use_graph=False, return_stats=True)
     ids_g = m.generate(**batch, max_new_tokens=n, do_sample=False, use_graph=True)
-    assert st["G"] == G and st["unique_prompts"] == 1 and st["n_shared_pages"] == 1848 // 64
+    assert st["G"] == G and st["unique_prompts"] == 1 and st["n_shared_pages"] == batch["input_ids"].shape[1] // 64 == 28
     assert torch.equal(ids_e, ids_g), "graph replay and eager decode disagree"
     assert all(torch.equal(ids_e[0], ids_e[r]) for r in range(G)), "rows of one greedy group must be identical"
     flips = _first_mismatch_ok(ids_e.cpu(), want, margins, tol=0.05)
