@@ -4,7 +4,7 @@
 // gradients exist for the norms or the base linears.
 #include "br_common.cuh"
 #include "../../include/bioreason_b200.h"
-#include "attn_common.cuh"
+
 
 namespace {
 
@@ -127,80 +127,6 @@ __global__ void qk_rope_bwd_kernel(bf16* __restrict__ dqkv, long long ldd, const
     }
 }
 
-// out[P, Rr] (+)= sum_m big[m, p] * small[m, r]; CTA = 64 p-columns x one chunk of rows; fp32 atomics across chunks.
-// big columns are addressed in 16-byte chunks: chunk c -> element offset (c * chunk_stride + chunk_offset) * 8
-// (chunk_stride 2 selects the gate or the up half of the blocked gate/up layout).
-template <int RR>
-__global__ void __launch_bounds__(128) xty_kernel(const bf16* __restrict__ big, long long ldb, const bf16* __restrict__ small, long long lds,
-                                                  float* __restrict__ out, long long ldo, int M, int P, int rows_per_cta, int chunk_stride,
-                                                  int chunk_offset, int transpose_out) {
-    using namespace attn;
-    constexpr int RCH = RR / 8;
-    __shared__ __align__(128) uint8_t sB[2][64 * 64 * 2];       // [m][p] 64 x 64 bf16
-    __shared__ __align__(128) uint8_t sS[2][64 * RR * 2];       // [m][r]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const int p0 = blockIdx.x * 64;
-    const int m_lo = blockIdx.y * rows_per_cta, m_hi = min(M, m_lo + rows_per_cta);
-    float acc[RR / 8][4];
-#pragma unroll
-    for (int i = 0; i < RR / 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-    auto issue = [&](int m0, int st) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {                         // 64 rows x 8 chunks
-            const int c = tid + i * 128, r = c >> 3, ch = c & 7;
-            const bool ok = (m0 + r) < m_hi;
-            const bf16* src = big + (long long)(ok ? m0 + r : 0) * ldb + ((long long)(p0 / 8 + ch) * chunk_stride + chunk_offset) * 8;
-            cp_async16(sB[st] + ((r * 8 + (ch ^ (r & 7))) << 4), src, ok);
-        }
-        for (int c = tid; c < 64 * RCH; c += 128) {
-            const int r = c / RCH, ch = c % RCH;
-            const bool ok = (m0 + r) < m_hi;
-            const bf16* src = small + (long long)(ok ? m0 + r : 0) * lds + ch * 8;
-            cp_async16(sS[st] + ((r * RCH + (RCH >= 8 ? (ch ^ (r & 7)) : ch)) << 4), src, ok);
-        }
-    };
-    const int n_it = (m_hi - m_lo + 63) / 64;
-    if (n_it > 0) issue(m_lo, 0);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-    for (int it = 0; it < n_it; ++it) {
-        const int st = it & 1;
-        if (it + 1 < n_it) issue(m_lo + (it + 1) * 64, st ^ 1);
-        cp_async_commit();
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {                      // 16 rows of m per k-step
-            uint32_t a[4];
-            {   // A[p][m] = big[m][p]: transposed fragments from the [m][p] tile
-                const int r = kk * 16 + (lane & 7) + (lane >> 4) * 8, ch = warp * 2 + ((lane >> 3) & 1);
-                ldsm_x4_t(a, sB[st] + ((r * 8 + (ch ^ (r & 7))) << 4));
-            }
-#pragma unroll
-            for (int np = 0; np < RR / 16; ++np) {
-                uint32_t f[4];
-                const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, ch = np * 2 + (lane >> 4);
-                ldsm_x4_t(f, sS[st] + ((r * RCH + (RCH >= 8 ? (ch ^ (r & 7)) : ch)) << 4));
-                mma16816(acc[2 * np], a, f[0], f[1]);
-                mma16816(acc[2 * np + 1], a, f[2], f[3]);
-            }
-        }
-        cp_async_wait<0>();
-        __syncthreads();
-    }
-    const int pa = p0 + warp * 16 + g, pb = pa + 8;
-#pragma unroll
-    for (int nt = 0; nt < RR / 8; ++nt) {
-        const int r = nt * 8 + 2 * t;
-        if (transpose_out) {
-            if (pa < P) { atomicAdd(out + (long long)r * ldo + pa, acc[nt][0]); atomicAdd(out + (long long)(r + 1) * ldo + pa, acc[nt][1]); }
-            if (pb < P) { atomicAdd(out + (long long)r * ldo + pb, acc[nt][2]); atomicAdd(out + (long long)(r + 1) * ldo + pb, acc[nt][3]); }
-        } else {
-            if (pa < P) { atomicAdd(out + (long long)pa * ldo + r, acc[nt][0]); atomicAdd(out + (long long)pa * ldo + r + 1, acc[nt][1]); }
-            if (pb < P) { atomicAdd(out + (long long)pb * ldo + r, acc[nt][2]); atomicAdd(out + (long long)pb * ldo + r + 1, acc[nt][3]); }
-        }
-    }
-}
-
 // out[N, M] = in[M, N]^T (bf16), rows of `out` beyond... (plain tiled transpose; out row stride ldo >= M)
 __global__ void transpose_kernel(const bf16* __restrict__ in, long long ldi, bf16* __restrict__ out, long long ldo, int M, int N) {
     __shared__ bf16 tile[32][33];
@@ -273,22 +199,6 @@ int br_qk_rope_bwd(void* dqkv, int64_t ldd, const void* qk_pre, int64_t ldp, int
     const long long warps = (long long)M * (n_q_heads + n_k_heads); const int wpb = 8;
     qk_rope_bwd_kernel<128><<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
         (bf16*)dqkv, ldd, (const bf16*)qk_pre, ldp, M, n_q_heads, n_k_heads, (const bf16*)q_norm_w, (const bf16*)k_norm_w, positions, theta, eps);
-    BR_CHECK_LAUNCH();
-    return BR_OK;
-}
-
-int br_xty_accumulate(const void* big, int64_t ldb, const void* small, int64_t lds, float* out, int64_t ldo, int M, int P, int Rr, int chunk_stride,
-                      int chunk_offset, int transpose_out, void* stream) {
-    BR_CHECK_ARG(M > 0 && P % 64 == 0 && (Rr == 16 || Rr == 32 || Rr == 64), "xty: P %% 64 == 0 and Rr in {16, 32, 64} (P=%d Rr=%d)", P, Rr);
-    BR_CHECK_ARG(ldb % 8 == 0 && lds % 8 == 0, "xty: strides %% 8");
-    int chunks = (4 * br_num_sms() + (P / 64) - 1) / (P / 64);
-    int rows_per_cta = ((M + chunks - 1) / chunks + 63) / 64 * 64;
-    if (rows_per_cta < 256) rows_per_cta = 256;
-    dim3 grid(P / 64, (M + rows_per_cta - 1) / rows_per_cta);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (Rr == 16) xty_kernel<16><<<grid, 128, 0, st>>>((const bf16*)big, ldb, (const bf16*)small, lds, out, ldo, M, P, rows_per_cta, chunk_stride, chunk_offset, transpose_out);
-    else if (Rr == 32) xty_kernel<32><<<grid, 128, 0, st>>>((const bf16*)big, ldb, (const bf16*)small, lds, out, ldo, M, P, rows_per_cta, chunk_stride, chunk_offset, transpose_out);
-    else xty_kernel<64><<<grid, 128, 0, st>>>((const bf16*)big, ldb, (const bf16*)small, lds, out, ldo, M, P, rows_per_cta, chunk_stride, chunk_offset, transpose_out);
     BR_CHECK_LAUNCH();
     return BR_OK;
 }

@@ -421,18 +421,6 @@ def qk_rope_bwd_(dqkv, qk_pre, n_q, n_k, head_dim, q_norm_w, k_norm_w, positions
     return dqkv
 
 
-def xty_accumulate_(out, big, small, *, P=None, chunk_stride=1, chunk_offset=0, transpose_out=False):
-    """out (fp32) += big[:, cols]^T @ small; out is [P, Rr] (or [Rr, P] if transpose_out)."""
-    M = big.shape[0]
-    Rr = small.shape[1]
-    if P is None:
-        P = big.shape[1]
-    assert out.dtype == torch.float32 and out.stride(-1) == 1
-    check(lib().br_xty_accumulate(ptr(big), _row_major_2d(big), ptr(small), _row_major_2d(small), ptr(out, "float*"), out.stride(0), M, P, Rr,
-                                  chunk_stride, chunk_offset, 1 if transpose_out else 0, _stream()), "xty_accumulate")
-    return out
-
-
 _LORA_WS = {}
 
 

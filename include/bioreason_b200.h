@@ -231,8 +231,6 @@ int br_swiglu_bwd(const void* gu, int64_t ldgu, const void* dact, int64_t ldda, 
 /* in place on the q and k head columns of dqkv: inverse RoPE then per-head RMSNorm backward (qk_pre = pre-norm q|k) */
 int br_qk_rope_bwd(void* dqkv, int64_t ldd, const void* qk_pre, int64_t ldp, int M, int n_q_heads, int n_k_heads, int head_dim,
                    const void* q_norm_w, const void* k_norm_w, const int32_t* positions, float theta, float eps, void* stream);
-/* out[P, Rr] += big[M, P]^T . small[M, Rr] (fp32 atomics; LoRA dA / dB).  big columns are taken in 16-byte chunks
- * (c * chunk_stride + chunk_offset); transpose_out writes out[Rr, P] instead. */
 /* LoRA weight gradients on tcgen05 (deterministic):  product[P, N] = big[M, P]^T . small[M, N] over the M tokens (both token-major,
  * bf16, read as MN-major tensor-core operands), then  dst (+)= the blocks the segments name.
  *   mode 0: segment i adds product rows [row_lo, row_hi), columns [col_lo, col_lo + n_cols) into dst[(row - row_lo) * ld + col - col_lo]
@@ -244,8 +242,6 @@ typedef struct br_lora_grad_seg { float* dst; int64_t ld; int32_t row_lo, row_hi
 int64_t br_lora_grad_workspace_bytes(void);
 int br_lora_grad_tn(const void* big, int64_t ldb, const void* small, int64_t lds, int M, int P, int N, int mode,
                     const br_lora_grad_seg* segs, int n_seg, void* workspace, void* stream);
-int br_xty_accumulate(const void* big, int64_t ldb, const void* small, int64_t lds, float* out, int64_t ldo, int M, int P, int Rr,
-                      int chunk_stride, int chunk_offset, int transpose_out, void* stream);
 int br_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int M, int N, void* stream);
 int br_colsum_accumulate(const void* in, int64_t ldi, float* out, int M, int N, void* stream);
 

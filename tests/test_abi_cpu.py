@@ -47,11 +47,16 @@ def test_sass_is_blackwell_native(built_lib):
         pytest.skip("cuobjdump not available")
     # every contraction of the path -- GEMMs, decode weight streaming, flash attention forward / backward, LoRA gradients -- must be
     # tcgen05 (UTCHMMA) fed by TMA (UTMALDG) with TMEM accumulators (LDTM), and must NOT contain the legacy mma.sync path (HMMA)
-    for name in ("gemm_tc5.o", "decode_gemm_tc5.o", "attn_fwd_tc5.o", "attn_bwd_tc5.o", "lora_grad_tc5.o"):
+    objs = ("gemm_tc5.o", "decode_gemm_tc5.o", "attn_fwd_tc5.o", "attn_bwd_tc5.o", "lora_grad_tc5.o")
+    for name in objs:
         sass = subprocess.run([cuobjdump, "-sass", os.path.join(os.path.dirname(built_lib), name)], capture_output=True, text=True).stdout
         for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
             assert mnemonic in sass, (name, mnemonic)
         assert "HMMA." not in sass.replace("UTCHMMA", ""), f"{name} still contains mma.sync (HMMA)"
+    # ... and nothing else on the dense path may carry mma.sync: the round-1 attention and x^T y kernels are gone
+    for name in ("attn_fwd.o", "attn_bwd.o", "backward_rows.o", "elementwise.o", "grpo_loss.o"):
+        sass = subprocess.run([cuobjdump, "-sass", os.path.join(os.path.dirname(built_lib), name)], capture_output=True, text=True).stdout
+        assert "HMMA." not in sass, f"{name} contains mma.sync (HMMA)"
     # P / dS / P^T operands are written to tensor memory by the softmax threads (tcgen05.st)
     for name in ("attn_fwd_tc5.o", "attn_bwd_tc5.o"):
         sass = subprocess.run([cuobjdump, "-sass", os.path.join(os.path.dirname(built_lib), name)], capture_output=True, text=True).stdout

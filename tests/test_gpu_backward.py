@@ -93,38 +93,52 @@ def test_attn_bwd(ops, B, L, nq, nkv):
         assert r < 2e-2, f"{name} rel err {r}"
 
 
-def test_xty_transpose_colsum(ops):
+def test_lora_grad_tn_transpose_colsum(ops):
+    """The tcgen05 TN GEMM behind the LoRA gradients (both operands MN-major, split-K without atomics): all three epilogue modes,
+    accumulation into the destination, strided views, bit-reproducibility; plus the transpose and column-sum helpers."""
     torch.manual_seed(3)
     M, P = 1000, 512
     big = torch.randn(M, P).bfloat16().cuda()
-    for Rr in (32, 64, 16):
+    for Rr in (32, 64, 16, 96):
         small = torch.randn(M, Rr).bfloat16().cuda()
         ref = big.float().T @ small.float()
         out = torch.zeros(P, Rr, device="cuda")
-        ops.xty_accumulate_(out, big, small)
+        ops.lora_grad_tn(big, small, [(out, 0, P, 0, Rr)])
         assert _rel(out, ref) < 1e-3
-        ops.xty_accumulate_(out, big, small)                                    # accumulates
+        ops.lora_grad_tn(big, small, [(out, 0, P, 0, Rr)])                        # accumulates
         assert _rel(out, 2 * ref) < 1e-3
         outT = torch.zeros(Rr, P, device="cuda")
-        ops.xty_accumulate_(outT, big, small, transpose_out=True)
+        ops.lora_grad_tn(big, small, [(outT, 0, P, 0, Rr)], mode=1)
         assert _rel(outT, ref.T) < 1e-3
-    # strided small / big views and the gate/up chunk selection
-    t = torch.randn(M, 96).bfloat16().cuda()
-    out = torch.zeros(256, 32, device="cuda")
-    ops.xty_accumulate_(out, big[:, 128:384], t[:, 32:64])
-    assert _rel(out, big[:, 128:384].float().T @ t[:, 32:64].float()) < 1e-3
-    gu = torch.randn(M, 2 * 256).bfloat16().cuda()
+        again = torch.zeros(Rr, P, device="cuda")
+        ops.lora_grad_tn(big, small, [(again, 0, P, 0, Rr)], mode=1)
+        assert torch.equal(again, outT), "split-K reduction must be bit-reproducible"
+    # block-diagonal segments of a fused product (the q | k | v layout) on strided column views, long M (split-K across many CTAs)
+    M2 = 5000
+    big2 = torch.randn(M2, 384).bfloat16().cuda(); t = torch.randn(M2, 96).bfloat16().cuda()
+    dq, dk, dv = torch.zeros(256, 32, device="cuda"), torch.zeros(64, 32, device="cuda"), torch.zeros(64, 32, device="cuda")
+    ops.lora_grad_tn(big2, t, [(dq, 0, 256, 0, 32), (dk, 256, 320, 32, 32), (dv, 320, 384, 64, 32)])
+    full = big2.float().T @ t.float()
+    assert _rel(dq, full[:256, :32]) < 1e-3 and _rel(dk, full[256:320, 32:64]) < 1e-3 and _rel(dv, full[320:, 64:]) < 1e-3
+    ov = torch.zeros(256, 32, device="cuda")
+    ops.lora_grad_tn(big2[:, 128:384], t[:, 32:64], [(ov, 0, 256, 0, 32)])
+    assert _rel(ov, big2[:, 128:384].float().T @ t[:, 32:64].float()) < 1e-3
+    # gate/up-blocked rows (blocks of 16 = 8 gate | 8 up)
+    gu = torch.randn(M, 2 * 256).bfloat16().cuda(); t2 = torch.randn(M, 64).bfloat16().cuda()
     g4 = gu.float().view(M, 32, 2, 8)
-    for off in (0, 1):
-        out = torch.zeros(256, 32, device="cuda")
-        ops.xty_accumulate_(out, gu, t[:, :32], P=256, chunk_stride=2, chunk_offset=off)
-        assert _rel(out, g4[:, :, off].reshape(M, 256).T @ t[:, :32].float()) < 1e-3
+    og, ou = torch.zeros(256, 32, device="cuda"), torch.zeros(256, 32, device="cuda")
+    ops.lora_grad_tn(gu, t2, [(og, 0, 512, 0, 32), (ou, 0, 512, 32, 32)], mode=2)
+    assert _rel(og, g4[:, :, 0].reshape(M, 256).T @ t2[:, :32].float()) < 1e-3
+    assert _rel(ou, g4[:, :, 1].reshape(M, 256).T @ t2[:, 32:].float()) < 1e-3
     x = torch.randn(77, 130).bfloat16().cuda()
     xt = ops.transpose(x)
     assert xt.shape == (130, 80) and torch.equal(xt[:, :77], x.T) and xt[:, 77:].abs().sum() == 0
     cs = torch.zeros(P, device="cuda")
     ops.colsum_accumulate_(cs, big)
     assert _rel(cs, big.float().sum(0)) < 1e-3
+    cs2 = torch.zeros(P, device="cuda")
+    ops.colsum_accumulate_(cs2, big)
+    assert torch.equal(cs, cs2)
 
 
 @pytest.mark.parametrize("cfg_name,B,n_seq,dna_len,text_len,C", [("tiny", 2, 1, [12, 9], [20, 14], 6), ("small", 3, 2, 40, [50, 66, 41], 9)])
