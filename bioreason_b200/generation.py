@@ -231,7 +231,8 @@ class RolloutEngine:
             St.scratch = ops.skinny_scratch(max(cfg.vocab_size, 2 * cfg.intermediate_size), dev)
             splits_shared = min(int(os.environ.get("BR_ATTN_SS", 8)), n_shared) if n_shared > 0 else 0
             splits_private = int(os.environ.get("BR_ATTN_SP", 2)) if n_shared > 0 else 8
-            cap = 3 * torch.cuda.get_device_properties(dev).multi_processor_count      # the fused kernel's merger items need co-residency
+            per_sm = 2 if os.environ.get("BR_DECODE_ATTN_TC5", "0") not in ("0", "") else 3     # CTAs of the fused attention an SM can hold
+            cap = per_sm * torch.cuda.get_device_properties(dev).multi_processor_count      # the fused kernel's merger items need co-residency
             n_items = lambda ss, sp: (R // G) * Hkv * ss + R * Hkv * sp
             while n_items(splits_shared, splits_private) > cap and (splits_shared > 1 or splits_private > 1):
                 if splits_private > 1 and (splits_private >= splits_shared or splits_shared <= 1):

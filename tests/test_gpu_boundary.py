@@ -101,7 +101,7 @@ def test_reference_call_sequence_through_compat(compat_path, tmp_path):
                                 processing_class=FakeTok(tc.eos_token_id))
     before = {k: v.detach().clone() for k, v in model.state_dict().items() if "lora_B" in k}
     loss = trainer.training_step(dict(batch, examples=examples))
-    assert torch.isfinite(loss) and set(seen_kwargs) == {"answer", "dna_sequences"}
+    assert torch.isfinite(loss) and set(seen_kwargs) == {"prompts", "answer", "dna_sequences"}      # prompts= plus every other dataset column
     assert trainer.reward_d2h_bytes == 4 * 6 * 8                                                 # completion ids went to the host once
     ck = os.path.join(str(tmp_path), "checkpoint-1", "pytorch_model.bin")
     assert os.path.exists(ck) and os.path.exists(os.path.join(str(tmp_path), "checkpoint-1", "config.json"))
