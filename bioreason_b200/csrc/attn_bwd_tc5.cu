@@ -7,21 +7,23 @@
 //   dq kernel   : CTA = 128-query tile of one (row, query head); loops over the key tiles it can see.
 //                   S  = Q K^T              (SS: both operands K-major in shared memory)
 //                   dP = dO V^T             (SS)
-//                   dS = P o (dP - delta) * scale   by 128 threads (thread <-> query row == TMEM lane), bf16 into TMEM over dP
+//                   dS = P o (dP - delta) * scale   by 256 threads (two per query row == TMEM lane, 64 key columns each), bf16 into TMEM over dP
 //                   dQ += dS K              (TS: A = dS in TENSOR MEMORY, B = the K tile as it landed, MN-major descriptor)
 //                 also computes delta = rowsum(dO o O) for its rows and publishes it for the dk/dv kernel.
 //   dk/dv kernel: CTA = 128-key tile of one (row, kv head); loops over the query heads of the group and the query tiles that
 //                 can see the keys; dK and dV accumulate in TMEM for the whole loop.
 //                   S^T  = K Q^T,  dP^T = V dO^T                 (SS)
-//                   P^T, dS^T (thread <-> key row) bf16 into TMEM over S^T / dP^T
+//                   P^T, dS^T (two threads per key row) bf16 into TMEM over S^T / dP^T -- each thread inside its own 64-column range
 //                   dV += P^T dO,  dK += dS^T Q                  (TS; dO and Q tiles are MN-major B operands)
 // TMEM: 384 / 512 columns; one CTA per SM (192 KB of shared memory: two resident tiles + a 2-stage ring of two streamed tiles).
+// The element-wise stage (one exp2 per score: ~16 k MUFU operations per 128 x 128 tile) bounds the tile period, not the tensor pipe; it
+// runs on 8 warps with both tcgen05.ld of a chunk in flight (the first version used 4 warps: 22 % / 34 % tensor-pipe active under ncu).
 #include "br_common.cuh"
 #include "../../include/bioreason_b200.h"
 
 namespace {
 
-constexpr int D = 128, BT = 128, NTHREADS = 192;
+constexpr int D = 128, BT = 128, NTHREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 element-wise (two threads per TMEM lane)
 constexpr int BLK = 128 * 128;            // bytes of a [128 rows x 64 cols] swizzled block
 constexpr int TILE = 2 * BLK;             // a 128 x 128 bf16 tile
 constexpr float LOG2E = 1.4426950408889634f;
@@ -52,7 +54,9 @@ __device__ __forceinline__ void mma_ts_mnmajor(uint32_t tmem_d, uint32_t tmem_a,
     constexpr uint32_t idesc = br::make_idesc_bf16_major(128, 128, 0, 1);
 #pragma unroll
     for (int kk = 0; kk < BT / 16; ++kk)
-        br::tc_mma_bf16_ts(tmem_d, tmem_a + kk * 8, br::make_sw128_mnmajor_desc(b_addr + kk * 2048, BLK, 1024), idesc, accumulate || kk != 0);
+        // the packed bf16 operand of K-range [64 h, 64 h + 64) sits in the first 32 columns of accumulator columns [64 h, 64 h + 64):
+        // each of the two threads of a lane writes inside its own column range (no thread overwrites what another still has to read)
+        br::tc_mma_bf16_ts(tmem_d, tmem_a + (kk >> 2) * 64 + (kk & 3) * 8, br::make_sw128_mnmajor_desc(b_addr + kk * 2048, BLK, 1024), idesc, accumulate || kk != 0);
 }
 __device__ __forceinline__ void tma_tile(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int col0, int row0) {
     br::tma_load_2d(dst, tm, bar, col0, row0);
@@ -73,7 +77,7 @@ __device__ __forceinline__ void store_row_bf16(bf16* dst, const uint32_t (&r)[32
 // =====================================================================================================================
 // dq kernel
 // =====================================================================================================================
-constexpr int DQ_OFF_Q = 0, DQ_OFF_DO = TILE, DQ_OFF_K = 2 * TILE, DQ_OFF_V = 4 * TILE, DQ_OFF_BAR = 6 * TILE;
+constexpr int DQ_OFF_Q = 0, DQ_OFF_DO = TILE, DQ_OFF_K = 2 * TILE, DQ_OFF_V = 4 * TILE, DQ_OFF_RED = 6 * TILE, DQ_OFF_BAR = DQ_OFF_RED + 256 * 4;
 constexpr int DQ_SMEM = DQ_OFF_BAR + 256 + 1024;
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -81,6 +85,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const __grid_constant__ CUtensorMap tmDO, const BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* s_red = reinterpret_cast<float*>(smem + DQ_OFF_RED);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_OFF_BAR);
     uint64_t* qdo_full = bars;            // 1
     uint64_t* k_full = bars + 1;          // 2
@@ -109,7 +114,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         br::tma_prefetch_desc(&tmQ); br::tma_prefetch_desc(&tmK); br::tma_prefetch_desc(&tmV); br::tma_prefetch_desc(&tmDO);
         br::mbar_init(qdo_full, 1);
         for (int s = 0; s < 2; ++s) { br::mbar_init(&k_full[s], 1); br::mbar_init(&v_full[s], 1); br::mbar_init(&k_empty[s], 1); br::mbar_init(&v_empty[s], 1); }
-        br::mbar_init(sdp_full, 1); br::mbar_init(ds_full, 4); br::mbar_init(dq_final, 1);
+        br::mbar_init(sdp_full, 1); br::mbar_init(ds_full, 8); br::mbar_init(dq_final, 1);
         br::mbar_fence_init();
     }
     if (warp == 1) { br::tmem_alloc(tmem_slot, 512); br::tmem_relinquish(); }
@@ -160,26 +165,31 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             br::tc_commit(dq_final);
         }
     } else {
+        // two threads per query row: warps 2..5 handle key columns [0, 64) of the tile, warps 6..9 columns [64, 128)
         const int lane_grp = warp & 3;
+        const int half = (warp - 2) >> 2, col0 = half * 64;
         const int row = lane_grp * 32 + lane;
         const int i_glob = q0 + row;
         const bool row_ok = i_glob < p.L;
         const uint32_t lane_off = (uint32_t)(lane_grp * 32) << 16;
         const long long tok = (long long)b * p.L + i_glob;
-        // ---- delta = rowsum(dO o O) for this query row (fp32), published for the dk/dv kernel
+        // ---- delta = rowsum(dO o O) for this query row (fp32; each thread half of the head dim), published for the dk/dv kernel
         float delta = 0.f;
         if (row_ok) {
-            const uint4* op = reinterpret_cast<const uint4*>(p.o + tok * p.ldo + (long long)h * D);
-            const uint4* dp = reinterpret_cast<const uint4*>(p.dout + tok * p.lddo + (long long)h * D);
+            const uint4* op = reinterpret_cast<const uint4*>(p.o + tok * p.ldo + (long long)h * D + col0);
+            const uint4* dp = reinterpret_cast<const uint4*>(p.dout + tok * p.lddo + (long long)h * D + col0);
 #pragma unroll 4
-            for (int c = 0; c < D / 8; ++c) {
+            for (int c = 0; c < D / 16; ++c) {
                 const uint4 a = __ldg(op + c), g = __ldg(dp + c);
                 const float2 a0 = br::unpack_bf16(a.x), a1 = br::unpack_bf16(a.y), a2 = br::unpack_bf16(a.z), a3 = br::unpack_bf16(a.w);
                 const float2 g0 = br::unpack_bf16(g.x), g1 = br::unpack_bf16(g.y), g2 = br::unpack_bf16(g.z), g3 = br::unpack_bf16(g.w);
                 delta += a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y + a3.x * g3.x + a3.y * g3.y;
             }
-            p.delta[((long long)b * p.Hq + h) * p.L + i_glob] = delta;
         }
+        s_red[half * 128 + row] = delta;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        delta = s_red[row] + s_red[128 + row];                          // fixed order: both threads of the row get the same value
+        if (row_ok && half == 0) p.delta[((long long)b * p.Hq + h) * p.L + i_glob] = delta;
         const float lse2 = row_ok ? p.lse[((long long)b * p.Hq + h) * p.L + i_glob] * LOG2E : INFINITY;
         const float delta_s = delta * p.scale;
         for (int t = 0; t < n_tiles; ++t) {
@@ -187,18 +197,18 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const bool need_mask = (k0 < ks) || (k0 + BT > ke) || (k0 + BT - 1 > q0);
             br::mbar_wait(sdp_full, t & 1);
             br::tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < BT; c += 32) {
+#pragma unroll
+            for (int c = 0; c < 64; c += 32) {
                 uint32_t rs[32], rp[32];
-                br::tmem_ld_32x32(tm_s + lane_off + c, rs);
-                br::tmem_ld_32x32(tm_dp + lane_off + c, rp);
+                br::tmem_ld_32x32(tm_s + lane_off + col0 + c, rs);
+                br::tmem_ld_32x32(tm_dp + lane_off + col0 + c, rp);
                 br::tmem_ld_wait();
                 uint32_t pk[16];
 #pragma unroll
                 for (int e = 0; e < 32; e += 2) {
                     float x0 = __uint_as_float(rs[e]) * p.scale_log2 - lse2, x1 = __uint_as_float(rs[e + 1]) * p.scale_log2 - lse2;
                     if (need_mask) {
-                        const int j = k0 + c + e;
+                        const int j = k0 + col0 + c + e;
                         x0 = ((j >= ks) && (j < ke) && (j <= i_glob)) ? x0 : -INFINITY;
                         x1 = ((j + 1 >= ks) && (j + 1 < ke) && (j + 1 <= i_glob)) ? x1 : -INFINITY;
                     }
@@ -206,27 +216,27 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     const float d0 = p0 * fmaf(__uint_as_float(rp[e]), p.scale, -delta_s), d1 = p1 * fmaf(__uint_as_float(rp[e + 1]), p.scale, -delta_s);
                     pk[e >> 1] = br::pack_bf16(d0, d1);
                 }
-                br::tmem_st_32x16(tm_dp + lane_off + (c >> 1), pk);       // dS over the consumed dP columns
+                br::tmem_st_32x16(tm_dp + lane_off + col0 + (c >> 1), pk);   // dS over the consumed dP columns of this thread's own range
             }
             br::tmem_st_wait();
             br::tc_fence_before();
             __syncwarp();
             if (lane == 0) br::mbar_arrive(ds_full);
         }
-        bf16* dq_row = p.dq + tok * p.lddq + (long long)h * D;
+        bf16* dq_row = p.dq + tok * p.lddq + (long long)h * D + col0;
         if (n_tiles > 0) {
             br::mbar_wait(dq_final, 0);
             br::tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < D; c += 32) {
+#pragma unroll
+            for (int c = 0; c < 64; c += 32) {
                 uint32_t r[32];
-                br::tmem_ld_32x32(tm_dq + lane_off + c, r);
+                br::tmem_ld_32x32(tm_dq + lane_off + col0 + c, r);
                 br::tmem_ld_wait();
                 if (row_ok) store_row_bf16(dq_row + c, r, 1.f);
             }
         } else if (row_ok) {
 #pragma unroll
-            for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dq_row + c) = make_uint4(0, 0, 0, 0);
+            for (int c = 0; c < 64; c += 8) *reinterpret_cast<uint4*>(dq_row + c) = make_uint4(0, 0, 0, 0);
         }
     }
     br::tc_fence_before();
@@ -271,7 +281,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         br::tma_prefetch_desc(&tmQ); br::tma_prefetch_desc(&tmK); br::tma_prefetch_desc(&tmV); br::tma_prefetch_desc(&tmDO);
         br::mbar_init(kv_full, 1);
         for (int s = 0; s < 2; ++s) { br::mbar_init(&q_full[s], 1); br::mbar_init(&do_full[s], 1); br::mbar_init(&qdo_empty[s], 1); }
-        br::mbar_init(sdp_full, 1); br::mbar_init(pds_full, 4); br::mbar_init(acc_final, 1);
+        br::mbar_init(sdp_full, 1); br::mbar_init(pds_full, 8); br::mbar_init(acc_final, 1);
         br::mbar_fence_init();
     }
     if (warp == 1) { br::tmem_alloc(tmem_slot, 512); br::tmem_relinquish(); }
@@ -322,59 +332,60 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             br::tc_commit(acc_final);
         }
     } else {
+        // two threads per key row: warps 2..5 handle query columns [0, 64) of the tile, warps 6..9 columns [64, 128)
         const int lane_grp = warp & 3;
+        const int half = (warp - 2) >> 2, col0 = half * 64;
         const int row = lane_grp * 32 + lane;                              // key row inside the tile == TMEM lane
-        const int et = threadIdx.x - 64;                                   // 0..127
+        const int et = threadIdx.x - 64;                                   // 0..255
         const int j_glob = key0 + row;
         const bool key_ok = (j_glob >= ks) && (j_glob < ke);
         const uint32_t lane_off = (uint32_t)(lane_grp * 32) << 16;
-        // per-query vectors of the next iteration, one element per thread, fetched one iteration ahead
-        auto fetch_vec = [&](int it, float& l2, float& ds) {
+        // per-query vectors of the next iteration, one element per thread (threads 0..127: lse, 128..255: delta), fetched one iteration ahead
+        auto fetch_vec = [&](int it) -> float {
             const int h = hk * GQ + it / per_head, ib = jb + it % per_head;
-            const int i = ib * BT + et;
-            l2 = INFINITY; ds = 0.f;
+            const int i = ib * BT + (et & 127);
             if (it < iters && i < p.L) {
                 const long long off = ((long long)b * p.Hq + h) * p.L + i;
-                l2 = __ldg(p.lse + off) * LOG2E; ds = __ldg(p.delta + off) * p.scale;
+                return et < 128 ? __ldg(p.lse + off) * LOG2E : __ldg(p.delta + off) * p.scale;
             }
+            return et < 128 ? INFINITY : 0.f;
         };
-        float nl2, nds;
-        fetch_vec(0, nl2, nds);
+        float nv = fetch_vec(0);
         for (int it = 0; it < iters; ++it) {
             const int s = it & 1;
             const int ib = jb + it % per_head;
             const int q0 = ib * BT;
             float* v_l2 = s_vec + s * 256; float* v_ds = v_l2 + 128;
-            v_l2[et] = nl2; v_ds[et] = nds;
-            fetch_vec(it + 1, nl2, nds);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            v_l2[et] = nv;                                                 // et >= 128 lands in v_ds[et - 128]
+            nv = fetch_vec(it + 1);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             const bool need_mask = (ib == jb) || (key0 < ks) || (key0 + BT > ke) || (q0 + BT > p.L);
             br::mbar_wait(sdp_full, it & 1);
             br::tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < BT; c += 32) {
+#pragma unroll
+            for (int c = 0; c < 64; c += 32) {
                 uint32_t rs[32], rp[32];
-                br::tmem_ld_32x32(tm_s + lane_off + c, rs);
-                br::tmem_ld_32x32(tm_dp + lane_off + c, rp);
+                br::tmem_ld_32x32(tm_s + lane_off + col0 + c, rs);
+                br::tmem_ld_32x32(tm_dp + lane_off + col0 + c, rp);
                 br::tmem_ld_wait();
                 uint32_t pk[16], dk_[16];
 #pragma unroll
                 for (int e = 0; e < 32; e += 4) {
-                    const float4 l4 = *reinterpret_cast<const float4*>(v_l2 + c + e), d4 = *reinterpret_cast<const float4*>(v_ds + c + e);
+                    const float4 l4 = *reinterpret_cast<const float4*>(v_l2 + col0 + c + e), d4 = *reinterpret_cast<const float4*>(v_ds + col0 + c + e);
                     const float ll[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
                     float pr[4], dsv[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         float x = __uint_as_float(rs[e + u]) * p.scale_log2 - ll[u];
-                        if (need_mask) { const int i = q0 + c + e + u; x = (key_ok && j_glob <= i) ? x : -INFINITY; }   // i >= L rows carry lse = +inf
+                        if (need_mask) { const int i = q0 + col0 + c + e + u; x = (key_ok && j_glob <= i) ? x : -INFINITY; }   // i >= L rows carry lse = +inf
                         pr[u] = ex2(x);
                         dsv[u] = pr[u] * fmaf(__uint_as_float(rp[e + u]), p.scale, -dd[u]);
                     }
                     pk[e >> 1] = br::pack_bf16(pr[0], pr[1]); pk[(e >> 1) + 1] = br::pack_bf16(pr[2], pr[3]);
                     dk_[e >> 1] = br::pack_bf16(dsv[0], dsv[1]); dk_[(e >> 1) + 1] = br::pack_bf16(dsv[2], dsv[3]);
                 }
-                br::tmem_st_32x16(tm_s + lane_off + (c >> 1), pk);        // P^T over the consumed S^T columns
-                br::tmem_st_32x16(tm_dp + lane_off + (c >> 1), dk_);      // dS^T over the consumed dP^T columns
+                br::tmem_st_32x16(tm_s + lane_off + col0 + (c >> 1), pk);    // P^T over the consumed S^T columns of this thread's own range
+                br::tmem_st_32x16(tm_dp + lane_off + col0 + (c >> 1), dk_);  // dS^T over the consumed dP^T columns
             }
             br::tmem_st_wait();
             br::tc_fence_before();
@@ -383,24 +394,24 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         const bool row_ok = j_glob < p.L;
         const long long tok = (long long)b * p.L + j_glob;
-        bf16* dk_row = p.dk + tok * p.lddk + (long long)hk * D;
-        bf16* dv_row = p.dv + tok * p.lddv + (long long)hk * D;
+        bf16* dk_row = p.dk + tok * p.lddk + (long long)hk * D + col0;
+        bf16* dv_row = p.dv + tok * p.lddv + (long long)hk * D + col0;
         if (iters > 0) {
             br::mbar_wait(acc_final, 0);
             br::tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < D; c += 32) {
+#pragma unroll
+            for (int c = 0; c < 64; c += 32) {
                 uint32_t r[32];
-                br::tmem_ld_32x32(tm_dv + lane_off + c, r);
+                br::tmem_ld_32x32(tm_dv + lane_off + col0 + c, r);
                 br::tmem_ld_wait();
                 if (row_ok) store_row_bf16(dv_row + c, r, 1.f);
-                br::tmem_ld_32x32(tm_dk + lane_off + c, r);
+                br::tmem_ld_32x32(tm_dk + lane_off + col0 + c, r);
                 br::tmem_ld_wait();
                 if (row_ok) store_row_bf16(dk_row + c, r, 1.f);
             }
         } else if (row_ok) {
 #pragma unroll
-            for (int c = 0; c < D; c += 8) { *reinterpret_cast<uint4*>(dk_row + c) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(dv_row + c) = make_uint4(0, 0, 0, 0); }
+            for (int c = 0; c < 64; c += 8) { *reinterpret_cast<uint4*>(dk_row + c) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(dv_row + c) = make_uint4(0, 0, 0, 0); }
         }
     }
     br::tc_fence_before();

@@ -4,14 +4,14 @@
 // row b attends keys j in [kv_start[b], kv_end[b]) (one contiguous window: left pads / post-EOS tail are outside), j <= i when causal;
 // optional log-sum-exp output for the backward.
 //
-// One CTA = one 128-query tile of one (batch row, query head); 192 threads:
+// One CTA = one 128-query tile of one (batch row, query head); 320 threads:
 //   warp 0      TMA producer : Q tile once; K and V tiles (128 keys x D, 128B-swizzled 64-column boxes) through 2- or 3-stage rings
 //   warp 1      MMA issuer   : S_j = Q K_j^T   (tcgen05.mma M=128 N=128, both operands K-major in shared memory) into one of two
 //                              TMEM score buffers, then O += P_{j-1} V_{j-1} with P read from TENSOR MEMORY (A operand in TMEM, packed
 //                              bf16 written by the softmax threads over the score buffer they just consumed) and V as an MN-major
 //                              shared-memory operand (the TMA tile [keys, d] as it lands: no transposed copy of V anywhere).
 //                              QK_j is issued before PV_{j-1}, so the tensor pipe computes the next scores while tile j-1 is in softmax.
-//   warps 2..5  softmax      : thread <-> query row (TMEM lane): tcgen05.ld of the row, mask, running max in the log2 domain with
+//   warps 2..9  softmax      : TWO threads per query row (TMEM lane), 64 score columns each: tcgen05.ld, mask, running max in the log2 domain with
 //                              LAZY rescaling (the accumulator row in TMEM is only rescaled when the max grew by more than 2^8, so
 //                              the O round trip through registers leaves the critical path), exp2, bf16 pack, tcgen05.st of P, row sums
 //                              in fp32; at the end O / l -> bf16 rows, LSE.
@@ -21,7 +21,7 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, NTHREADS = 192;
+constexpr int BM = 128, BN = 128, NTHREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two threads per query row)
 
 struct FwdParams {
     bf16* o; long long ldo;
@@ -42,7 +42,8 @@ struct SL {
     static constexpr int OFF_Q = 0;
     static constexpr int OFF_K = TILE;
     static constexpr int OFF_V = OFF_K + NST * TILE;
-    static constexpr int OFF_BAR = OFF_V + NST * TILE;
+    static constexpr int OFF_RED = OFF_V + NST * TILE;   // [2 tiles][2 halves][128 rows] row maxima + [2][128] row sums (fp32)
+    static constexpr int OFF_BAR = OFF_RED + 768 * 4;
     static constexpr int TOTAL = OFF_BAR + 256 + 1024;
 };
 
@@ -53,6 +54,7 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     using L = SL<D>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* s_red = reinterpret_cast<float*>(smem + L::OFF_RED);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
     uint64_t* q_full = bars;                       // 1
     uint64_t* k_full = bars + 1;                   // NST
@@ -82,7 +84,7 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         br::tma_prefetch_desc(&tmQ); br::tma_prefetch_desc(&tmK); br::tma_prefetch_desc(&tmV);
         br::mbar_init(q_full, 1);
         for (int s = 0; s < L::NST; ++s) { br::mbar_init(&k_full[s], 1); br::mbar_init(&k_empty[s], 1); br::mbar_init(&v_full[s], 1); br::mbar_init(&v_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { br::mbar_init(&s_full[s], 1); br::mbar_init(&p_full[s], 4); br::mbar_init(&pv_done[s], 1); }
+        for (int s = 0; s < 2; ++s) { br::mbar_init(&s_full[s], 1); br::mbar_init(&p_full[s], 8); br::mbar_init(&pv_done[s], 1); }
         br::mbar_fence_init();
     }
     if (warp == 1) { br::tmem_alloc(tmem_slot, 512); br::tmem_relinquish(); }
@@ -149,7 +151,8 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     for (int kk = 0; kk < BN / 16; ++kk) {
                         // 16 keys = 2 groups of 8 rows (SBO = 1024 B); the D/64 blocks of 64 d-columns are L::BLK bytes apart (LBO)
                         const uint64_t bdesc = br::make_sw128_mnmajor_desc(v_addr + kk * 2048, L::BLK, 1024);
-                        br::tc_mma_bf16_ts(tmem_o, tmem_p + kk * 8, bdesc, idesc_pv, (u | kk) != 0);
+                        // P of keys [64 h, 64 h + 64) sits in the first 32 columns of score columns [64 h, 64 h + 64) (see the softmax warps)
+                        br::tc_mma_bf16_ts(tmem_o, tmem_p + (kk >> 2) * 64 + (kk & 3) * 8, bdesc, idesc_pv, (u | kk) != 0);
                     }
                     br::tc_commit(&v_empty[sp]);
                     br::tc_commit(&pv_done[u & 1]);
@@ -158,78 +161,74 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
         }
     } else {
-        // ===================== softmax / correction / epilogue (warps 2..5) =====================
+        // ===================== softmax / correction / epilogue (warps 2..9) =====================
+        // TWO threads per query row: warps 2..5 own score columns [0, 64) of their rows, warps 6..9 columns [64, 128) (the exp2 work of
+        // a 128 x 128 tile is ~16 k MUFU operations -- with one thread per row the softmax, not the tensor pipe, set the tile period:
+        // 14.8 % tensor-pipe active in the first ncu capture).  Each thread reads its 64 scores once (two tcgen05.ld in flight), the
+        // two halves exchange their row maxima through shared memory, and each writes its packed P into the first 32 columns of ITS
+        // OWN 64-column range, so no thread ever writes a column another thread still has to read.
         const int lane_grp = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int col0 = half * 64;
         const int row = lane_grp * 32 + lane;                 // query row inside the tile == TMEM lane
         const int i_glob = q0 + row;
         const uint32_t lane_off = (uint32_t)(lane_grp * 32) << 16;
-        float m_used = -INFINITY, l = 0.f;
+        float m_used = -INFINITY, l = 0.f;                    // l: this thread's half of the row sum
         for (int t = 0; t < n_tiles; ++t) {
-            const int nbase = (jb_lo + t) * BN;
-            const uint32_t tmem_s = tmem_base + (t & 1) * BN + lane_off;
-            const bool need_mask = (nbase < ks) || (nbase + BN > ke) || (CAUSAL && nbase + BN - 1 > q0);
+            const int nbase = (jb_lo + t) * BN + col0;
+            const uint32_t tmem_s = tmem_base + (t & 1) * BN + lane_off + col0;
+            const bool need_mask = (nbase - col0 < ks) || (nbase - col0 + BN > ke) || (CAUSAL && nbase - col0 + BN - 1 > q0);
             br::mbar_wait(&s_full[t & 1], (t >> 1) & 1);
             br::tc_fence_after();
-            // ---- pass 1: row maximum (log2 domain)
+            uint32_t r0[32], r1[32];
+            br::tmem_ld_32x32(tmem_s, r0);
+            br::tmem_ld_32x32(tmem_s + 32, r1);
+            br::tmem_ld_wait();
             float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
-                uint32_t r[32];
-                br::tmem_ld_32x32(tmem_s + c, r);
-                br::tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    float v = __uint_as_float(r[e]) * p.scale_log2;
-                    if (need_mask) {
-                        const int j = nbase + c + e;
-                        const bool ok = (j >= ks) && (j < ke) && (!CAUSAL || j <= i_glob);
-                        v = ok ? v : -INFINITY;
-                    }
-                    mx = fmaxf(mx, v);
+            for (int e = 0; e < 32; ++e) {
+                float a = __uint_as_float(r0[e]) * p.scale_log2, c = __uint_as_float(r1[e]) * p.scale_log2;
+                if (need_mask) {
+                    const int ja = nbase + e, jc = nbase + 32 + e;
+                    a = ((ja >= ks) && (ja < ke) && (!CAUSAL || ja <= i_glob)) ? a : -INFINITY;
+                    c = ((jc >= ks) && (jc < ke) && (!CAUSAL || jc <= i_glob)) ? c : -INFINITY;
                 }
+                r0[e] = __float_as_uint(a); r1[e] = __float_as_uint(c);
+                mx = fmaxf(mx, fmaxf(a, c));
             }
-            const float m_new = fmaxf(m_used, mx);
+            float* red = s_red + (t & 1) * 256;               // double-buffered: a fast thread may be one tile ahead of its partner
+            red[half * 128 + row] = mx;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float m_new = fmaxf(m_used, fmaxf(mx, red[(half ^ 1) * 128 + row]));
             // lazy rescale: keep the stale maximum while the new one is within 2^8 of it (p <= 256: exact enough in bf16 / fp32 sums)
             const bool grow = (m_new > m_used + 8.f) || (m_used == -INFINITY && m_new > -INFINITY);
             float alpha = 1.f;
             if (grow) { alpha = (m_used == -INFINITY) ? 0.f : ex2(m_used - m_new); m_used = m_new; }
             const float ms = (m_used == -INFINITY) ? 0.f : m_used;
-            // ---- pass 2: p = exp2(s - m), row sum, bf16 pack, P -> TMEM over the first half of this score buffer
             float rsum = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
-                uint32_t r[32];
-                br::tmem_ld_32x32(tmem_s + c, r);
-                br::tmem_ld_wait();
-                uint32_t pk[16];
+            uint32_t pk[32];
 #pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                    float v0 = __uint_as_float(r[e]) * p.scale_log2 - ms, v1 = __uint_as_float(r[e + 1]) * p.scale_log2 - ms;
-                    if (need_mask) {
-                        const int j = nbase + c + e;
-                        const bool ok0 = (j >= ks) && (j < ke) && (!CAUSAL || j <= i_glob);
-                        const bool ok1 = (j + 1 >= ks) && (j + 1 < ke) && (!CAUSAL || j + 1 <= i_glob);
-                        v0 = ok0 ? v0 : -INFINITY; v1 = ok1 ? v1 : -INFINITY;
-                    }
-                    const float p0 = ex2(v0), p1 = ex2(v1);
-                    rsum += p0 + p1;
-                    pk[e >> 1] = br::pack_bf16(p0, p1);
-                }
-                br::tmem_st_32x16(tmem_s + (c >> 1), pk);     // columns [c/2, c/2 + 16): always behind the columns already consumed
+            for (int e = 0; e < 32; e += 2) {
+                const float p0 = ex2(__uint_as_float(r0[e]) - ms), p1 = ex2(__uint_as_float(r0[e + 1]) - ms);
+                const float p2 = ex2(__uint_as_float(r1[e]) - ms), p3 = ex2(__uint_as_float(r1[e + 1]) - ms);
+                rsum += (p0 + p1) + (p2 + p3);
+                pk[e >> 1] = br::pack_bf16(p0, p1); pk[16 + (e >> 1)] = br::pack_bf16(p2, p3);
             }
+            br::tmem_st_32x32(tmem_s, pk);                    // 64 keys of P, packed, over the first 32 of this thread's own 64 columns
             l = l * alpha + rsum;
-            // ---- correction: rescale the accumulator row only when some row of this warp moved its maximum
+            // ---- correction: this thread's half of the accumulator row, only when some row of the warp moved its maximum
             if (t > 0 && __any_sync(0xffffffffu, grow)) {
                 br::mbar_wait(&pv_done[(t - 1) & 1], ((t - 1) >> 1) & 1);
                 br::tc_fence_after();
-#pragma unroll 1
-                for (int c = 0; c < D; c += 32) {
+                constexpr int OH = D / 2;                      // accumulator columns per half
+#pragma unroll
+                for (int c = 0; c < OH; c += 32) {
                     uint32_t r[32];
-                    br::tmem_ld_32x32(tmem_o + lane_off + c, r);
+                    br::tmem_ld_32x32(tmem_o + lane_off + half * OH + c, r);
                     br::tmem_ld_wait();
 #pragma unroll
                     for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
-                    br::tmem_st_32x32(tmem_o + lane_off + c, r);
+                    br::tmem_st_32x32(tmem_o + lane_off + half * OH + c, r);
                 }
             }
             br::tmem_st_wait();
@@ -237,17 +236,21 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             __syncwarp();
             if (lane == 0) br::mbar_arrive(&p_full[t & 1]);
         }
-        // ---- epilogue: O / l -> bf16 row, log-sum-exp
-        bf16* orow = p.o + ((long long)b * p.L + i_glob) * p.ldo + (long long)h * D;
+        // ---- epilogue: O / l -> bf16 row (each thread its half of the columns), log-sum-exp
+        constexpr int OH = D / 2;
+        s_red[512 + half * 128 + row] = l;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        l += s_red[512 + (half ^ 1) * 128 + row];
+        bf16* orow = p.o + ((long long)b * p.L + i_glob) * p.ldo + (long long)h * D + half * OH;
         const bool row_ok = i_glob < p.L;
         if (n_tiles > 0) {
             br::mbar_wait(&pv_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
             br::tc_fence_after();
             const float inv = l > 0.f ? 1.f / l : 0.f;
-#pragma unroll 1
-            for (int c = 0; c < D; c += 32) {
+#pragma unroll
+            for (int c = 0; c < OH; c += 32) {
                 uint32_t r[32];
-                br::tmem_ld_32x32(tmem_o + lane_off + c, r);
+                br::tmem_ld_32x32(tmem_o + lane_off + half * OH + c, r);
                 br::tmem_ld_wait();
                 if (row_ok) {
 #pragma unroll
@@ -263,9 +266,9 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
         } else if (row_ok) {
 #pragma unroll
-            for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(orow + c) = make_uint4(0, 0, 0, 0);
+            for (int c = 0; c < OH; c += 8) *reinterpret_cast<uint4*>(orow + c) = make_uint4(0, 0, 0, 0);
         }
-        if (p.lse && row_ok) {
+        if (p.lse && row_ok && half == 0) {
             const float LN2 = 0.6931471805599453f;
             p.lse[((long long)b * p.Hq + h) * p.L + i_glob] = l > 0.f ? m_used * LN2 + logf(l) : INFINITY;
         }

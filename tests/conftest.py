@@ -34,7 +34,7 @@ def _built_library(request):
 @pytest.fixture(scope="session")
 def golden():
     import torch
-    return torch.load(os.path.join(ROOT, "tests", "golden", "reference_tiny.pt"), weights_only=False)
+    return torch.load(os.path.join(ROOT, "tests", "golden", "reference_tiny.pt"), weights_only=True)
 
 
 @pytest.fixture(scope="session")
