@@ -4,24 +4,28 @@
 // row b attends keys j in [kv_start[b], kv_end[b]) (one contiguous window: left pads / post-EOS tail are outside), j <= i when causal;
 // optional log-sum-exp output for the backward.
 //
-// One CTA = one 128-query tile of one (batch row, query head); 320 threads:
-//   warp 0      TMA producer : Q tile once; K and V tiles (128 keys x D, 128B-swizzled 64-column boxes) through 2- or 3-stage rings
-//   warp 1      MMA issuer   : S_j = Q K_j^T   (tcgen05.mma M=128 N=128, both operands K-major in shared memory) into one of two
+// One CTA = one 128-query tile of one (batch row, query head); 192 threads, TWO CTAs per SM (256 TMEM columns, ~97 KB of shared memory each):
+//   warp 0      TMA producer : Q tile once; K and V tiles (64 keys x D, 128B-swizzled 64-column boxes) through 2- or 3-stage rings
+//   warp 1      MMA issuer   : S_j = Q K_j^T   (tcgen05.mma M=128 N=64, both operands K-major in shared memory) into one of two
 //                              TMEM score buffers, then O += P_{j-1} V_{j-1} with P read from TENSOR MEMORY (A operand in TMEM, packed
 //                              bf16 written by the softmax threads over the score buffer they just consumed) and V as an MN-major
 //                              shared-memory operand (the TMA tile [keys, d] as it lands: no transposed copy of V anywhere).
 //                              QK_j is issued before PV_{j-1}, so the tensor pipe computes the next scores while tile j-1 is in softmax.
-//   warps 2..9  softmax      : TWO threads per query row (TMEM lane), 64 score columns each: tcgen05.ld, mask, running max in the log2 domain with
+//   warps 2..5  softmax      : one thread per query row (TMEM lane), 64 score columns: tcgen05.ld, mask, running max in the log2 domain with
 //                              LAZY rescaling (the accumulator row in TMEM is only rescaled when the max grew by more than 2^8, so
 //                              the O round trip through registers leaves the critical path), exp2, bf16 pack, tcgen05.st of P, row sums
 //                              in fp32; at the end O / l -> bf16 rows, LSE.
-// TMEM: 2 x 128 score columns + D accumulator columns (512 allocated: one CTA per SM, ~165 KB of shared memory).
+// Why two small CTAs instead of one large one: the per-tile chain (scores ready -> tcgen05.ld -> max -> exp2 -> tcgen05.st -> P ready -> MMA)
+// is a latency chain, and the exp2 work (16 k MUFU operations per 128 x 128 scores = 1024 clocks per SM) is as long as the two MMAs of
+// the tile.  One CTA with 256 softmax threads in lock-step (row-max exchange through shared memory + a 256-thread barrier per tile) ran
+// the tensor pipe at 26 %: its warps all sat in the same phase at the same time.  Two independent CTAs with 64-key tiles need no
+// exchange (one thread owns a whole row of the tile) and interleave their phases on the SM's MUFU / tensor / TMEM-load units.
 #include "br_common.cuh"
 #include "../../include/bioreason_b200.h"
 
 namespace {
 
-constexpr int BM = 128, BN = 128, NTHREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two threads per query row)
+constexpr int BM = 128, BN = 64, NTHREADS = 192;           // warp 0 TMA, warp 1 MMA, warps 2..5 softmax (one thread per query row)
 
 struct FwdParams {
     bf16* o; long long ldo;
@@ -36,25 +40,26 @@ __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32
 template <int D>
 struct SL {
     static constexpr int NB = D / 64;                  // 64-column (128-byte) swizzled blocks per row
-    static constexpr int BLK = 128 * 128;              // bytes of one [128 rows x 64 cols] block
-    static constexpr int TILE = NB * BLK;              // one Q / K / V tile
+    static constexpr int BLKQ = BM * 128;              // bytes of one [128 rows x 64 cols] block of Q
+    static constexpr int BLKK = BN * 128;              // bytes of one [64 keys x 64 cols] block of K / V
+    static constexpr int TILEQ = NB * BLKQ;
+    static constexpr int TILEK = NB * BLKK;
     static constexpr int NST = (D == 128) ? 2 : 3;     // K and V ring depth
     static constexpr int OFF_Q = 0;
-    static constexpr int OFF_K = TILE;
-    static constexpr int OFF_V = OFF_K + NST * TILE;
-    static constexpr int OFF_RED = OFF_V + NST * TILE;   // [2 tiles][2 halves][128 rows] row maxima + [2][128] row sums (fp32)
-    static constexpr int OFF_BAR = OFF_RED + 768 * 4;
+    static constexpr int OFF_K = TILEQ;
+    static constexpr int OFF_V = OFF_K + NST * TILEK;
+    static constexpr int OFF_BAR = OFF_V + NST * TILEK;
     static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+    static constexpr int TMEM_COLS = 256;              // 2 x 64 score columns + D accumulator columns (192 or 256 -> 256)
 };
 
 template <int D, bool CAUSAL>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, 2)
 attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                     const FwdParams p) {
     using L = SL<D>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float* s_red = reinterpret_cast<float*>(smem + L::OFF_RED);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
     uint64_t* q_full = bars;                       // 1
     uint64_t* k_full = bars + 1;                   // NST
@@ -84,10 +89,10 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         br::tma_prefetch_desc(&tmQ); br::tma_prefetch_desc(&tmK); br::tma_prefetch_desc(&tmV);
         br::mbar_init(q_full, 1);
         for (int s = 0; s < L::NST; ++s) { br::mbar_init(&k_full[s], 1); br::mbar_init(&k_empty[s], 1); br::mbar_init(&v_full[s], 1); br::mbar_init(&v_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { br::mbar_init(&s_full[s], 1); br::mbar_init(&p_full[s], 8); br::mbar_init(&pv_done[s], 1); }
+        for (int s = 0; s < 2; ++s) { br::mbar_init(&s_full[s], 1); br::mbar_init(&p_full[s], 4); br::mbar_init(&pv_done[s], 1); }
         br::mbar_fence_init();
     }
-    if (warp == 1) { br::tmem_alloc(tmem_slot, 512); br::tmem_relinquish(); }
+    if (warp == 1) { br::tmem_alloc(tmem_slot, L::TMEM_COLS); br::tmem_relinquish(); }
     br::tc_fence_before();
     __syncthreads();
     br::tc_fence_after();
@@ -98,20 +103,20 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // ===================== TMA producer =====================
         if (lane == 0 && n_tiles > 0) {
             const int row_q = b * p.L + q0;
-            br::mbar_expect_tx(q_full, L::TILE);
+            br::mbar_expect_tx(q_full, L::TILEQ);
 #pragma unroll
-            for (int nb = 0; nb < L::NB; ++nb) br::tma_load_2d(smem + L::OFF_Q + nb * L::BLK, &tmQ, q_full, h * D + nb * 64, row_q);
+            for (int nb = 0; nb < L::NB; ++nb) br::tma_load_2d(smem + L::OFF_Q + nb * L::BLKQ, &tmQ, q_full, h * D + nb * 64, row_q);
             int s = 0; uint32_t ph = 0;
             for (int t = 0; t < n_tiles; ++t) {
                 const int row_k = b * p.L + (jb_lo + t) * BN;
                 br::mbar_wait(&k_empty[s], ph ^ 1);
-                br::mbar_expect_tx(&k_full[s], L::TILE);
+                br::mbar_expect_tx(&k_full[s], L::TILEK);
 #pragma unroll
-                for (int nb = 0; nb < L::NB; ++nb) br::tma_load_2d(smem + L::OFF_K + s * L::TILE + nb * L::BLK, &tmK, &k_full[s], hk * D + nb * 64, row_k);
+                for (int nb = 0; nb < L::NB; ++nb) br::tma_load_2d(smem + L::OFF_K + s * L::TILEK + nb * L::BLKK, &tmK, &k_full[s], hk * D + nb * 64, row_k);
                 br::mbar_wait(&v_empty[s], ph ^ 1);
-                br::mbar_expect_tx(&v_full[s], L::TILE);
+                br::mbar_expect_tx(&v_full[s], L::TILEK);
 #pragma unroll
-                for (int nb = 0; nb < L::NB; ++nb) br::tma_load_2d(smem + L::OFF_V + s * L::TILE + nb * L::BLK, &tmV, &v_full[s], hk * D + nb * 64, row_k);
+                for (int nb = 0; nb < L::NB; ++nb) br::tma_load_2d(smem + L::OFF_V + s * L::TILEK + nb * L::BLKK, &tmV, &v_full[s], hk * D + nb * 64, row_k);
                 if (++s == L::NST) { s = 0; ph ^= 1; }
             }
         }
@@ -129,12 +134,12 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 if (t < n_tiles) {
                     br::mbar_wait(&k_full[s], ph);
                     br::tc_fence_after();
-                    const uint32_t k_addr = br::smem_u32(smem + L::OFF_K + s * L::TILE);
+                    const uint32_t k_addr = br::smem_u32(smem + L::OFF_K + s * L::TILEK);
                     const uint32_t tmem_s = tmem_base + (t & 1) * BN;
 #pragma unroll
                     for (int kk = 0; kk < D / 16; ++kk) {
-                        const uint32_t off = (kk >> 2) * L::BLK + (kk & 3) * 32;
-                        br::tc_mma_bf16(tmem_s, br::make_sw128_kmajor_desc(q_addr + off), br::make_sw128_kmajor_desc(k_addr + off), idesc_qk, kk != 0);
+                        const uint32_t qoff = (kk >> 2) * L::BLKQ + (kk & 3) * 32, koff = (kk >> 2) * L::BLKK + (kk & 3) * 32;
+                        br::tc_mma_bf16(tmem_s, br::make_sw128_kmajor_desc(q_addr + qoff), br::make_sw128_kmajor_desc(k_addr + koff), idesc_qk, kk != 0);
                     }
                     br::tc_commit(&s_full[t & 1]);
                     br::tc_commit(&k_empty[s]);
@@ -145,14 +150,14 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     br::mbar_wait(&p_full[u & 1], (u >> 1) & 1);
                     br::mbar_wait(&v_full[sp], php);
                     br::tc_fence_after();
-                    const uint32_t v_addr = br::smem_u32(smem + L::OFF_V + sp * L::TILE);
+                    const uint32_t v_addr = br::smem_u32(smem + L::OFF_V + sp * L::TILEK);
                     const uint32_t tmem_p = tmem_base + (u & 1) * BN;
 #pragma unroll
                     for (int kk = 0; kk < BN / 16; ++kk) {
-                        // 16 keys = 2 groups of 8 rows (SBO = 1024 B); the D/64 blocks of 64 d-columns are L::BLK bytes apart (LBO)
-                        const uint64_t bdesc = br::make_sw128_mnmajor_desc(v_addr + kk * 2048, L::BLK, 1024);
-                        // P of keys [64 h, 64 h + 64) sits in the first 32 columns of score columns [64 h, 64 h + 64) (see the softmax warps)
-                        br::tc_mma_bf16_ts(tmem_o, tmem_p + (kk >> 2) * 64 + (kk & 3) * 8, bdesc, idesc_pv, (u | kk) != 0);
+                        // 16 keys = 2 groups of 8 rows (SBO = 1024 B); the D/64 blocks of 64 d-columns are L::BLKK bytes apart (LBO)
+                        const uint64_t bdesc = br::make_sw128_mnmajor_desc(v_addr + kk * 2048, L::BLKK, 1024);
+                        // P (64 keys, packed bf16 pairs) sits in the first 32 columns of the score buffer it was computed from
+                        br::tc_mma_bf16_ts(tmem_o, tmem_p + kk * 8, bdesc, idesc_pv, (u | kk) != 0);
                     }
                     br::tc_commit(&v_empty[sp]);
                     br::tc_commit(&pv_done[u & 1]);
@@ -161,23 +166,16 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
         }
     } else {
-        // ===================== softmax / correction / epilogue (warps 2..9) =====================
-        // TWO threads per query row: warps 2..5 own score columns [0, 64) of their rows, warps 6..9 columns [64, 128) (the exp2 work of
-        // a 128 x 128 tile is ~16 k MUFU operations -- with one thread per row the softmax, not the tensor pipe, set the tile period:
-        // 14.8 % tensor-pipe active in the first ncu capture).  Each thread reads its 64 scores once (two tcgen05.ld in flight), the
-        // two halves exchange their row maxima through shared memory, and each writes its packed P into the first 32 columns of ITS
-        // OWN 64-column range, so no thread ever writes a column another thread still has to read.
-        const int lane_grp = warp & 3;
-        const int half = (warp - 2) >> 2;
-        const int col0 = half * 64;
+        // ===================== softmax / correction / epilogue (warps 2..5) =====================
+        const int lane_grp = warp & 3;                        // the TMEM lane quarter this warp may access
         const int row = lane_grp * 32 + lane;                 // query row inside the tile == TMEM lane
         const int i_glob = q0 + row;
         const uint32_t lane_off = (uint32_t)(lane_grp * 32) << 16;
-        float m_used = -INFINITY, l = 0.f;                    // l: this thread's half of the row sum
+        float m_used = -INFINITY, l = 0.f;                    // running maximum in units of RAW scores * scale_log2
         for (int t = 0; t < n_tiles; ++t) {
-            const int nbase = (jb_lo + t) * BN + col0;
-            const uint32_t tmem_s = tmem_base + (t & 1) * BN + lane_off + col0;
-            const bool need_mask = (nbase - col0 < ks) || (nbase - col0 + BN > ke) || (CAUSAL && nbase - col0 + BN - 1 > q0);
+            const int nbase = (jb_lo + t) * BN;
+            const uint32_t tmem_s = tmem_base + (t & 1) * BN + lane_off;
+            const bool need_mask = (nbase < ks) || (nbase + BN > ke) || (CAUSAL && nbase + BN - 1 > q0);
             br::mbar_wait(&s_full[t & 1], (t >> 1) & 1);
             br::tc_fence_after();
             uint32_t r0[32], r1[32];
@@ -185,50 +183,45 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             br::tmem_ld_32x32(tmem_s + 32, r1);
             br::tmem_ld_wait();
             float mx = -INFINITY;
+            if (need_mask) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                float a = __uint_as_float(r0[e]) * p.scale_log2, c = __uint_as_float(r1[e]) * p.scale_log2;
-                if (need_mask) {
+                for (int e = 0; e < 32; ++e) {
                     const int ja = nbase + e, jc = nbase + 32 + e;
-                    a = ((ja >= ks) && (ja < ke) && (!CAUSAL || ja <= i_glob)) ? a : -INFINITY;
-                    c = ((jc >= ks) && (jc < ke) && (!CAUSAL || jc <= i_glob)) ? c : -INFINITY;
+                    if (!((ja >= ks) && (ja < ke) && (!CAUSAL || ja <= i_glob))) r0[e] = 0xff800000u;      // -inf
+                    if (!((jc >= ks) && (jc < ke) && (!CAUSAL || jc <= i_glob))) r1[e] = 0xff800000u;
                 }
-                r0[e] = __float_as_uint(a); r1[e] = __float_as_uint(c);
-                mx = fmaxf(mx, fmaxf(a, c));
             }
-            float* red = s_red + (t & 1) * 256;               // double-buffered: a fast thread may be one tile ahead of its partner
-            red[half * 128 + row] = mx;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float m_new = fmaxf(m_used, fmaxf(mx, red[(half ^ 1) * 128 + row]));
+#pragma unroll
+            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[e]), __uint_as_float(r1[e])));
+            const float m_new = fmaxf(m_used, mx * p.scale_log2);          // scale > 0: the max commutes with the scaling
             // lazy rescale: keep the stale maximum while the new one is within 2^8 of it (p <= 256: exact enough in bf16 / fp32 sums)
             const bool grow = (m_new > m_used + 8.f) || (m_used == -INFINITY && m_new > -INFINITY);
             float alpha = 1.f;
             if (grow) { alpha = (m_used == -INFINITY) ? 0.f : ex2(m_used - m_new); m_used = m_new; }
             const float ms = (m_used == -INFINITY) ? 0.f : m_used;
-            float rsum = 0.f;
+            float rs0 = 0.f, rs1 = 0.f;
             uint32_t pk[32];
 #pragma unroll
             for (int e = 0; e < 32; e += 2) {
-                const float p0 = ex2(__uint_as_float(r0[e]) - ms), p1 = ex2(__uint_as_float(r0[e + 1]) - ms);
-                const float p2 = ex2(__uint_as_float(r1[e]) - ms), p3 = ex2(__uint_as_float(r1[e + 1]) - ms);
-                rsum += (p0 + p1) + (p2 + p3);
+                const float p0 = ex2(fmaf(__uint_as_float(r0[e]), p.scale_log2, -ms)), p1 = ex2(fmaf(__uint_as_float(r0[e + 1]), p.scale_log2, -ms));
+                const float p2 = ex2(fmaf(__uint_as_float(r1[e]), p.scale_log2, -ms)), p3 = ex2(fmaf(__uint_as_float(r1[e + 1]), p.scale_log2, -ms));
+                rs0 += p0 + p1; rs1 += p2 + p3;
                 pk[e >> 1] = br::pack_bf16(p0, p1); pk[16 + (e >> 1)] = br::pack_bf16(p2, p3);
             }
-            br::tmem_st_32x32(tmem_s, pk);                    // 64 keys of P, packed, over the first 32 of this thread's own 64 columns
-            l = l * alpha + rsum;
-            // ---- correction: this thread's half of the accumulator row, only when some row of the warp moved its maximum
+            br::tmem_st_32x32(tmem_s, pk);                    // 64 keys of P, packed, over the first 32 of the 64 score columns just read
+            l = l * alpha + (rs0 + rs1);
+            // ---- correction of the accumulator row, only when some row of the warp moved its maximum
             if (t > 0 && __any_sync(0xffffffffu, grow)) {
                 br::mbar_wait(&pv_done[(t - 1) & 1], ((t - 1) >> 1) & 1);
                 br::tc_fence_after();
-                constexpr int OH = D / 2;                      // accumulator columns per half
 #pragma unroll
-                for (int c = 0; c < OH; c += 32) {
+                for (int c = 0; c < D; c += 32) {
                     uint32_t r[32];
-                    br::tmem_ld_32x32(tmem_o + lane_off + half * OH + c, r);
+                    br::tmem_ld_32x32(tmem_o + lane_off + c, r);
                     br::tmem_ld_wait();
 #pragma unroll
                     for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
-                    br::tmem_st_32x32(tmem_o + lane_off + half * OH + c, r);
+                    br::tmem_st_32x32(tmem_o + lane_off + c, r);
                 }
             }
             br::tmem_st_wait();
@@ -236,21 +229,17 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             __syncwarp();
             if (lane == 0) br::mbar_arrive(&p_full[t & 1]);
         }
-        // ---- epilogue: O / l -> bf16 row (each thread its half of the columns), log-sum-exp
-        constexpr int OH = D / 2;
-        s_red[512 + half * 128 + row] = l;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        l += s_red[512 + (half ^ 1) * 128 + row];
-        bf16* orow = p.o + ((long long)b * p.L + i_glob) * p.ldo + (long long)h * D + half * OH;
+        // ---- epilogue: O / l -> bf16 row, log-sum-exp
+        bf16* orow = p.o + ((long long)b * p.L + i_glob) * p.ldo + (long long)h * D;
         const bool row_ok = i_glob < p.L;
         if (n_tiles > 0) {
             br::mbar_wait(&pv_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
             br::tc_fence_after();
             const float inv = l > 0.f ? 1.f / l : 0.f;
 #pragma unroll
-            for (int c = 0; c < OH; c += 32) {
+            for (int c = 0; c < D; c += 32) {
                 uint32_t r[32];
-                br::tmem_ld_32x32(tmem_o + lane_off + half * OH + c, r);
+                br::tmem_ld_32x32(tmem_o + lane_off + c, r);
                 br::tmem_ld_wait();
                 if (row_ok) {
 #pragma unroll
@@ -266,9 +255,9 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
         } else if (row_ok) {
 #pragma unroll
-            for (int c = 0; c < OH; c += 8) *reinterpret_cast<uint4*>(orow + c) = make_uint4(0, 0, 0, 0);
+            for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(orow + c) = make_uint4(0, 0, 0, 0);
         }
-        if (p.lse && row_ok && half == 0) {
+        if (p.lse && row_ok) {
             const float LN2 = 0.6931471805599453f;
             p.lse[((long long)b * p.Hq + h) * p.L + i_glob] = l > 0.f ? m_used * LN2 + logf(l) : INFINITY;
         }
@@ -278,7 +267,7 @@ attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     __syncthreads();
     if (warp == 1) {
         br::tc_fence_after();
-        br::tmem_dealloc(tmem_base, 512);
+        br::tmem_dealloc(tmem_base, L::TMEM_COLS);
     }
 }
 
@@ -287,7 +276,11 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, 
     using L = SL<D>;
     auto kern = attn_fwd_tc5_kernel<D, CAUSAL>;
     static bool done = false;
-    if (!done) { BR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL)); done = true; }
+    if (!done) {
+        BR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        BR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));       // two CTAs per SM
+        done = true;
+    }
     dim3 grid((p.L + BM - 1) / BM, p.Hq, p.B);
     kern<<<grid, NTHREADS, L::TOTAL, st>>>(tq, tk, tv, p);
     BR_CHECK_LAUNCH();
