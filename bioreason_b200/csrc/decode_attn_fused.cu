@@ -28,7 +28,7 @@ struct FusedParams {
     const int* cur_len;
     int R, G, Hq, Hkv, GQ;
     int n_shared_pages, SS, SP, n_slots;
-    float* part_o; float* part_lse; int* counters;      // [R,Hq,n_slots,D], [R,Hq,n_slots], [R*Hkv]
+    float* part_o; float* part_lse; int* counters;      // [R,Hq,n_slots,D], [R,Hq,n_slots], [2][R*Hkv] (arrivals, finished pollers)
     bf16* out; long long ldo;
     float scale_log2, theta, eps;
     long long* dbg;                      // optional [items, 16] globaltimer stamps (profiling aid)
@@ -527,39 +527,38 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p, c
     }
     }
     STAMP(5);
-    // ---- arrival counters: one per (row, kv head).  The private split-0 item of a (row, kv head) pair is its merger: it waits for
-    //      the other n_slots - 1 partials and merges them, so the 64 merges of a step run on 64 different CTAs in parallel
-    //      (a "last arriver merges" scheme serialises all 8 rows of a group on one late shared item).  All items of a launch are
-    //      co-resident (checked on the host), so the bounded spin cannot deadlock.
+    // ---- arrival counters: one per (row, kv head).  Every item publishes its partial and arrives; the SP private items of a
+    //      (row, kv head) pair then ALL merge -- each a contiguous share of the pair's GQ x D output -- so the 64 merges of a step run on
+    //      64 x SP CTAs and every thread has its whole gather (<= 32 slots of one float4 column) in flight in one L2 round trip.
+    //      (A single merger per pair needed three dependent rounds of loads: it was the tail of the launch, ~4 us after the last
+    //      arrival.)  All items of a launch are co-resident (checked on the host), so the bounded spin cannot deadlock.
     //      A row's GQ query vectors live in ONE warp (16 % GQ == 0), so a warp publishes its rows by itself: stores, __syncwarp, one
     //      release-reduction per row -- no CTA barrier, no fence, no returning atomic on the way out.
-    const bool merger = !shared_pass && split == 0;
-    if (!merger) {
-        __syncwarp();
-        if (warp_live) {
-            const int rows_in_warp = TC5 ? rows_per_unit : 16 / p.GQ; // legacy: a warp holds 16 / GQ rows; TC5: warp 0 wrote every row of the unit
-            const int rr = shared_pass ? (TC5 ? 0 : warp * rows_in_warp) + lane : 0;
-            if (lane < (shared_pass ? rows_in_warp : 1) && rr < rows_per_unit && row_base + rr < p.R)
-                asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.counters + (row_base + rr) * p.Hkv + kvh) : "memory");
-        }
-        STAMP(6); STAMP(7);
-        return;
+    __syncwarp();
+    if (warp_live) {
+        const int rows_in_warp = TC5 ? rows_per_unit : 16 / p.GQ; // legacy: a warp holds 16 / GQ rows; TC5: warp 0 wrote every row of the unit
+        const int rr = shared_pass ? (TC5 ? 0 : warp * rows_in_warp) + lane : 0;
+        if (lane < (shared_pass ? rows_in_warp : 1) && rr < rows_per_unit && row_base + rr < p.R)
+            asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.counters + (row_base + rr) * p.Hkv + kvh) : "memory");
     }
-    __syncthreads();                                                   // the merger's own partial (warp 0) is complete
+    if (shared_pass) { STAMP(6); STAMP(7); return; }
     if (tid == 0) {
         int* c = p.counters + row_base * p.Hkv + kvh;
         int seen;
-        do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(c) : "memory"); } while (seen < p.n_slots - 1);
-        *c = 0;                                                        // nobody touches it again before the next launch
+        do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(c) : "memory"); } while (seen < p.n_slots);
+        // the last of the SP pollers to get here resets both words for the next launch (nobody arrives or polls after that)
+        int* dn = p.counters + p.R * p.Hkv + row_base * p.Hkv + kvh;
+        if (atomicAdd(dn, 1) == p.SP - 1) { *c = 0; *dn = 0; }
     }
     __syncthreads();
     STAMP(6);
-    // merge of the n_slots partials of this (row, kv head): slot weights from the LSEs (one coalesced load per head, warp reductions),
-    // then every thread gathers its two float4 output chunks from all slots with up to 16 independent L2 loads in flight.
     {
-        float* s_w = reinterpret_cast<float*>(smem);                   // [GQ][32] (tile smem is free now)
+        float* s_w = reinterpret_cast<float*>(smem);                   // [GQ][32] slot weights (tile smem is free now)
         const int row = row_base;
-        for (int hl = warp; hl < p.GQ; hl += 2) {
+        const int per_row = p.GQ * (D / 4);                            // float4 chunks of this (row, kv head) output
+        const int lo = (per_row * split) / p.SP, hi = (per_row * (split + 1)) / p.SP;
+        // slot weights of the heads this share touches: softmax over the slots' LSEs (one coalesced load per head, warp reductions)
+        for (int hl = lo / (D / 4) + warp; hl <= (hi - 1) / (D / 4) && hi > lo; hl += 2) {
             const float* lse = p.part_lse + ((long long)row * p.Hq + kvh * p.GQ + hl) * p.n_slots;
             const float l = lane < p.n_slots ? __ldcg(lse + lane) : -INFINITY;
             const float mx = br::warp_max(l);
@@ -568,34 +567,24 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p, c
             s_w[hl * 32 + lane] = den > 0.f ? e / den : 0.f;
         }
         __syncthreads();
-        const int per_row = p.GQ * (D / 4);
-        for (int idx = tid; idx < per_row; idx += 2 * NT) {
-            const int idx2 = idx + NT;
-            const bool two = idx2 < per_row;
-            const int hlA = idx / (D / 4), dA = (idx % (D / 4)) * 4, hlB = two ? idx2 / (D / 4) : hlA, dB = two ? (idx2 % (D / 4)) * 4 : dA;
-            const float* poA = p.part_o + ((long long)row * p.Hq + kvh * p.GQ + hlA) * p.n_slots * D + dA;
-            const float* poB = p.part_o + ((long long)row * p.Hq + kvh * p.GQ + hlB) * p.n_slots * D + dB;
-            float4 accA = make_float4(0.f, 0.f, 0.f, 0.f), accB = accA;
-            for (int s0 = 0; s0 < p.n_slots; s0 += 8) {
-                float4 va[8], vb[8];
+        for (int idx = lo + tid; idx < hi; idx += NT) {
+            const int hl = idx / (D / 4), d0 = (idx % (D / 4)) * 4;
+            const float* po = p.part_o + ((long long)row * p.Hq + kvh * p.GQ + hl) * p.n_slots * D + d0;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+            for (int s0 = 0; s0 < p.n_slots; s0 += 16) {
+                float4 va[16];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const bool ok = s0 + j < p.n_slots;
-                    va[j] = ok ? __ldcg(reinterpret_cast<const float4*>(poA + (long long)(s0 + j) * D)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    vb[j] = (ok && two) ? __ldcg(reinterpret_cast<const float4*>(poB + (long long)(s0 + j) * D)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                for (int j = 0; j < 16; ++j)
+                    va[j] = (s0 + j < p.n_slots) ? __ldcg(reinterpret_cast<const float4*>(po + (long long)(s0 + j) * D)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {                          // fixed slot order: deterministic
-                    const float wa = (s0 + j < p.n_slots) ? s_w[hlA * 32 + s0 + j] : 0.f, wb = (s0 + j < p.n_slots) ? s_w[hlB * 32 + s0 + j] : 0.f;
-                    accA.x += wa * va[j].x; accA.y += wa * va[j].y; accA.z += wa * va[j].z; accA.w += wa * va[j].w;
-                    accB.x += wb * vb[j].x; accB.y += wb * vb[j].y; accB.z += wb * vb[j].z; accB.w += wb * vb[j].w;
+                for (int j = 0; j < 16; ++j) {                         // fixed slot order: deterministic
+                    const float w = (s0 + j < p.n_slots) ? s_w[hl * 32 + s0 + j] : 0.f;
+                    acc.x += w * va[j].x; acc.y += w * va[j].y; acc.z += w * va[j].z; acc.w += w * va[j].w;
                 }
             }
-            *reinterpret_cast<uint2*>(p.out + (long long)row * p.ldo + (long long)(kvh * p.GQ + hlA) * D + dA) =
-                make_uint2(br::pack_bf16(accA.x, accA.y), br::pack_bf16(accA.z, accA.w));
-            if (two)
-                *reinterpret_cast<uint2*>(p.out + (long long)row * p.ldo + (long long)(kvh * p.GQ + hlB) * D + dB) =
-                    make_uint2(br::pack_bf16(accB.x, accB.y), br::pack_bf16(accB.z, accB.w));
+            *reinterpret_cast<uint2*>(p.out + (long long)row * p.ldo + (long long)(kvh * p.GQ + hl) * D + d0) =
+                make_uint2(br::pack_bf16(acc.x, acc.y), br::pack_bf16(acc.z, acc.w));
         }
     }
     STAMP(7);
@@ -611,7 +600,7 @@ extern "C" {
 int br_decode_attn_fused_debug(long long* buf) { g_dbg = buf; return BR_OK; }
 
 int64_t br_decode_fused_workspace_bytes(int R, int n_q_heads, int n_kv_heads, int head_dim, int n_slots) {
-    return (int64_t)R * n_q_heads * n_slots * (head_dim + 1) * sizeof(float) + (int64_t)R * n_kv_heads * sizeof(int);
+    return (int64_t)R * n_q_heads * n_slots * (head_dim + 1) * sizeof(float) + 2 * (int64_t)R * n_kv_heads * sizeof(int);
 }
 
 int br_rope_table(float* out, int n_pos, int head_dim, float theta, void* stream) {

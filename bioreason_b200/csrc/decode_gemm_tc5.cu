@@ -364,7 +364,10 @@ int launch(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& tp, 
     using L = SL<BNX>;
     auto kern = skinny_tc5_kernel<BNX, RM>;
     static bool done = false;
-    if (!done) { BR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL)); done = true; }
+    if (!done) {
+        BR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        done = true;
+    }
     BR_CHECK_CUDA(br_launch_pdl(kern, dim3(grid), dim3(NTHREADS), (size_t)L::TOTAL, st, tw, tx, tp, p));
     return BR_OK;
 }

@@ -48,6 +48,51 @@ __device__ int find_bin(const int* hist, int nbins, int& k_rem, int* s_tmp) {
     return b;
 }
 
+// Fast selection of a SUPERSET of the k largest values (the common case; exactness comes from the consumer, which ranks the superset):
+// one shared-memory histogram over the distance to the maximum, bin = floor((max - v) * 32) -- monotone in v, so "all elements in bins
+// <= b*" (b* = the bin holding the k-th largest) contains the k largest and every tie of the k-th.  The exact 3-pass radix select over
+// the raw key bits (below) puts ~all logits of a chunk into a handful of exponent bins in its first pass (serialised shared-memory
+// atomics) and needs three histogram rounds; this needs one, with the counts spread over ~100 bins.  Values further than 64 below the
+// maximum are not counted (they can only matter when k exceeds everything closer, which falls back to the radix select).
+constexpr int FBINS = 2048;
+constexpr float FBIN_SCALE = 32.f;
+__device__ __forceinline__ int fast_bin(float mx, float v) {
+    const float d = (mx - v) * FBIN_SCALE;                       // NaN (mx = v = -inf) -> 0, +inf -> saturates
+    return d >= (float)(FBINS - 1) ? FBINS - 1 : __float2int_rd(d);
+}
+// warp 0: smallest bin b with count(bins <= b) >= k -> out[0] = b (or -1), out[1] = count(bins <= b)
+__device__ void find_bin_asc(const int* hist, int k, int* out) {
+    const int lane = threadIdx.x & 31;
+    int acc = 0, found = -1, cnt = 0;
+    for (int base = 0; base < FBINS - 32; base += 32) {          // the last bin (saturated values) is never counted
+        const int c = hist[base + lane];
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (acc + total >= k) {
+            const unsigned m = __ballot_sync(0xffffffffu, acc + incl >= k);
+            const int l = __ffs(m) - 1;
+            found = base + l; cnt = acc + __shfl_sync(0xffffffffu, incl, l);
+            break;
+        }
+        acc += total;
+    }
+    if (lane == 0) { out[0] = found; out[1] = cnt; }
+}
+__device__ __forceinline__ float block_max(float v, float* s_red) {   // all threads get the maximum; s_red: 32 floats
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    float m = lane < nw ? s_red[lane] : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __syncthreads();
+    return m;
+}
+
 // Stage 1 (many CTAs): each CTA owns a 4096-logit chunk of one row, keeps it in registers, finds the chunk's exact
 // top_k-th value by radix select on shared-memory histograms and emits every element >= that value (value, token id) --
 // a superset of the row's global top-k.  Stage 2 (sampler_kernel, one CTA per row) then works on <= chunks*CAND_CAP
@@ -76,6 +121,42 @@ __global__ void __launch_bounds__(256) sampler_partial_kernel(const float* __res
     }
     const int n_here = min(CHUNK, V - base);
     const int k = min(top_k, n_here);
+    float* cv = cand_val + ((long long)row * n_chunks + chunk) * CAND_CAP;
+    int* ci = cand_idx + ((long long)row * n_chunks + chunk) * CAND_CAP;
+    // ---- fast path: one histogram over the distance to the chunk maximum (see fast_bin)
+    {
+        __shared__ float s_red[32];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, v[i]);
+        mx = block_max(mx, s_red);
+        for (int i = tid; i < FBINS; i += 256) hist[i] = 0;
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        int bin[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            bin[i] = (base + i * 256 + tid < V) ? fast_bin(mx, v[i]) : FBINS - 1;
+            if (bin[i] < FBINS - 1) atomicAdd(&hist[bin[i]], 1);
+        }
+        __syncthreads();
+        if (warp == 0) find_bin_asc(hist, k, s_tmp);
+        __syncthreads();
+        const int bstar = s_tmp[0], cnt = s_tmp[1];
+        if (mx > -INFINITY && bstar >= 0 && cnt <= CAND_CAP) {                  // uniform across the CTA
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (bin[i] <= bstar) {
+                    const int s = atomicAdd(&s_count, 1);
+                    cv[s] = v[i]; ci[s] = base + i * 256 + tid;
+                }
+            }
+            for (int s = cnt + tid; s < CAND_CAP; s += 256) { cv[s] = -INFINITY; ci[s] = 0x7fffffff; }
+            return;
+        }
+        __syncthreads();
+    }
+    // ---- exact path (degenerate chunks: > CAND_CAP values within 1/32 of the k-th, or nothing finite)
     uint32_t prefix = 0; int k_rem = k;
     for (int pass = 0; pass < 3; ++pass) {
         const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
@@ -103,20 +184,38 @@ __global__ void __launch_bounds__(256) sampler_partial_kernel(const float* __res
         prefix = pass == 0 ? (uint32_t)b : (pass == 1 ? ((prefix << 11) | (uint32_t)b) : ((prefix << 10) | (uint32_t)b));
         __syncthreads();
     }
+    // values strictly above the k-th (fewer than k) always fit; ties OF the k-th fill the remaining slots in token-id order, so the
+    // emitted set does not depend on the order in which threads reach an atomic
     if (tid == 0) s_count = 0;
     __syncthreads();
-    float* cv = cand_val + ((long long)row * n_chunks + chunk) * CAND_CAP;
-    int* ci = cand_idx + ((long long)row * n_chunks + chunk) * CAND_CAP;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const int idx = base + i * 256 + tid;
-        if (idx < V && key[i] >= prefix) {
+        if (idx < V && key[i] > prefix) {
             const int s = atomicAdd(&s_count, 1);
             if (s < CAND_CAP) { cv[s] = v[i]; ci[s] = idx; }
         }
     }
     __syncthreads();
-    for (int s = min(s_count, CAND_CAP) + tid; s < CAND_CAP; s += 256) { cv[s] = -INFINITY; ci[s] = 0x7fffffff; }
+    int filled = min(s_count, CAND_CAP);
+    __shared__ int s_w[8];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        if (filled >= CAND_CAP) break;                                 // uniform across the CTA
+        const int idx = base + i * 256 + tid;
+        const bool tie = idx < V && key[i] == prefix;
+        const unsigned m = __ballot_sync(0xffffffffu, tie);
+        if (lane == 0) s_w[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const int c = s_w[w]; total += c; if (w < warp) before += c; }
+        const int slot = filled + before + __popc(m & ((1u << lane) - 1u));
+        if (tie && slot < CAND_CAP) { cv[slot] = v[i]; ci[slot] = idx; }
+        filled = min(CAND_CAP, filled + total);
+        __syncthreads();
+    }
+    for (int s = filled + tid; s < CAND_CAP; s += 256) { cv[s] = -INFINITY; ci[s] = 0x7fffffff; }
 }
 
 // Stage 2 / single-stage sampler.  cand_idx == nullptr: x is the full logits row (index = position).
@@ -166,6 +265,42 @@ __global__ void __launch_bounds__(1024) sampler_kernel(const float* __restrict__
         __syncthreads();
         choice = s_tmp[2];
     } else {
+      bool fast_done = false;
+      if (xi != nullptr && V <= 4 * (int)blockDim.x) {
+        // ---- fast path over the stage-1 candidates (<= 4 per thread): superset by distance-to-maximum bins, exact ranking below
+        float v[4]; int id[4]; int bin[4];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + i * blockDim.x;
+            const bool ok = idx < V;
+            v[i] = ok ? __ldcg(x + idx) : -INFINITY; id[i] = ok ? __ldcg(xi + idx) : 0x7fffffff;
+            mx = fmaxf(mx, v[i]);
+        }
+        mx = block_max(mx, r_val);
+        for (int i = tid; i < FBINS; i += blockDim.x) hist[i] = 0;
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            bin[i] = v[i] > -INFINITY ? fast_bin(mx, v[i]) : FBINS - 1;
+            if (bin[i] < FBINS - 1) atomicAdd(&hist[bin[i]], 1);
+        }
+        __syncthreads();
+        if (warp == 0) find_bin_asc(hist, top_k, s_tmp);
+        __syncthreads();
+        const int bstar = s_tmp[0], cnt = s_tmp[1];
+        __syncthreads();
+        if (mx > -INFINITY && bstar >= 0 && cnt <= MAXC) {                       // uniform across the CTA
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (bin[i] <= bstar) { const int s = atomicAdd(&s_count, 1); c_val[s] = v[i]; c_idx[s] = id[i]; }
+            }
+            fast_done = true;
+        }
+        __syncthreads();
+      }
+      if (!fast_done) {
         // ---- exact k-th largest key by 3-pass radix select
         uint32_t prefix = 0; int k_rem = top_k;
         for (int pass = 0; pass < 3; ++pass) {
@@ -202,16 +337,21 @@ __global__ void __launch_bounds__(1024) sampler_kernel(const float* __restrict__
             }
         }
         __syncthreads();
-        const int c = min(s_count, MAXC);
+      }
+        const int c_all = min(s_count, MAXC);
         // ---- rank sort: descending value, ties by ascending index
-        if (tid < c) {
+        if (tid < c_all) {
             const float v = c_val[tid]; const int id = c_idx[tid];
             int rank = 0;
-            for (int j = 0; j < c; ++j) rank += (c_val[j] > v) || (c_val[j] == v && c_idx[j] < id);
+            for (int j = 0; j < c_all; ++j) rank += (c_val[j] > v) || (c_val[j] == v && c_idx[j] < id);
             o_val[rank] = v; o_idx[rank] = id;
         }
         __syncthreads();
         if (tid == 0) {
+            // top-k with HF's tie rule (`scores < topk(scores)[..., -1]` are dropped: every value equal to the k-th stays); the
+            // collected set may be a superset (fast path) or exactly that set (radix path)
+            int c = min(top_k, c_all);
+            if (c > 0) { const float kth = o_val[c - 1]; while (c < c_all && o_val[c] == kth) ++c; }
             // softmax over the kept-by-top-k set at temperature T (fp32), descending order
             const float inv_t = 1.f / temperature;
             const float mx = o_val[0] * inv_t;

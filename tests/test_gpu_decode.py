@@ -162,6 +162,49 @@ def test_sampler_matches_hf_warpers(ops):
     assert torch.equal(nxt.cpu(), want) and fin[3].item() == 1
 
 
+@pytest.mark.parametrize("kind", ["narrow", "constant", "masked", "ties", "wide"])
+def test_sampler_two_stage_degenerate_distributions(ops, kind):
+    """The two-stage sampler picks its candidates from a histogram over the distance to the maximum and falls back to an exact radix
+    select when that is not selective (many values within 1/32 of the k-th).  Whatever path runs, the draw must equal the single-stage
+    exact sampler's and HF's warpers: logits with a tiny spread, constant rows, rows that are -inf except a few entries, massive ties."""
+    torch.manual_seed(11)
+    R, V, C = 8, 151936, 3
+    g = torch.Generator().manual_seed(5)
+    if kind == "narrow":
+        logits = torch.randn(R, V, generator=g) * 1e-3                      # everything within one bin of the maximum
+    elif kind == "constant":
+        logits = torch.zeros(R, V)                                           # 151 911 exact ties below 25 distinct small bumps
+        logits[:, torch.arange(25) * 6007 + 13] = torch.arange(1, 26).float() * 1e-4
+    elif kind == "masked":
+        logits = torch.full((R, V), float("-inf"))
+        idx = torch.randint(0, V, (R, 40), generator=g)
+        logits.scatter_(1, idx, torch.randn(R, 40, generator=g) * 3)
+    elif kind == "ties":
+        logits = torch.randn(R, V, generator=g).mul(4).round().div(4)        # quantised: hundreds of exact ties at every level
+    else:
+        logits = torch.randn(R, V, generator=g) * 30                        # far beyond the 64-unit histogram range
+    uni = torch.rand(C, R, generator=g)
+    fin = torch.zeros(R, dtype=torch.int32, device="cuda"); step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ws = ops.sample_workspace(R, V, "cuda")
+    for s_ in range(C):
+        step.fill_(s_)
+        a = torch.zeros(R, dtype=torch.int64, device="cuda"); b = torch.zeros_like(a)
+        kw = dict(temperature=0.6, top_k=20, top_p=0.95, do_sample=True, uniforms=uni.cuda(), step=step, max_steps=C, eos_id=-1, pad_id=0, finished=fin)
+        ops.sample_next(logits.cuda(), next_ids=a, **kw)
+        ops.sample_next(logits.cuda(), next_ids=b, workspace=ws, **kw)
+        assert torch.equal(a.cpu(), b.cpu()), kind
+        if kind not in ("constant", "ties", "narrow"):                       # HF keeps EVERY tie of the k-th value; same support here
+            ref, probs = _sampler_ref(logits, 0.6, 20, 0.95, uni[s_])
+            assert torch.all(probs.gather(1, a.cpu()[:, None]) > 0)
+        # greedy
+        ops.sample_next(logits.cuda(), do_sample=False, step=step, max_steps=C, eos_id=-1, pad_id=0, finished=fin, next_ids=b, workspace=ws)
+        assert torch.equal(b.cpu(), logits.argmax(-1)) or kind in ("ties", "constant", "narrow")
+        if kind in ("ties", "constant"):                                     # ties: the smallest token id among the maxima
+            mx = logits.max(-1, keepdim=True).values
+            first = (logits == mx).int().argmax(-1)
+            assert torch.equal(b.cpu(), first)
+
+
 def _first_mismatch_ok(got, want, margins, tol):
     """Greedy ids must be bit-exact except where the oracle's own top-2 margin is below the bf16 noise floor; after such
     a near-tie flip the continuations legitimately diverge, so comparison of that row stops there."""
