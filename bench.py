@@ -258,8 +258,9 @@ def run_b200(args):
     roofline = {"bound": "hbm", "kernel": "skinny_tc5_kernel (decode weight streaming, %d launches = all GEMMs of one token step for the group, CUDA-graph replay)" % n_k,
                 "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 4),
                 # dram__bytes_read+write per launch from the committed `ncu --set full` capture: 50.10 MB for the 49.81 MB down_proj launch and
-                # 31.59 MB for the 31.46 MB qkv launch (profiles/r01_ncu_full_skinny_tc5_kernel.txt) -> 1.005 x the algorithmic bytes
-                "traffic": int(1.005 * bytes_k / n_k), "traffic_source": "ncu capture ratio 1.005 (profiles/r01_ncu_full_skinny_tc5_kernel.txt)",
+                # dram read+write 31.6 MB for the 31.46 MB qkv launch, 21.1 / 20.97 (o), 102.9 / 99.6 (gate/up incl. 3.2 MB written), 50.1 / 49.8
+                # (down): profiles/r02_ncu_targets.txt -> 1.005 .. 1.03 x the algorithmic bytes; the launch-weighted mean is used
+                "traffic": int(1.012 * bytes_k / n_k), "traffic_source": "ncu --set full capture, dram bytes / algorithmic bytes = 1.012 (profiles/r02_ncu_targets.txt)",
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                 "bytes_per_launch_avg": int(bytes_k / n_k), "launch_us_avg": round(ms_k * 1e3 / n_k, 2),
                 "phases": {"rollout_s": round(decode_s, 4), "rollout_hbm_frac": round(work["decode_bytes"] / max(decode_s, 1e-9) / 1e9 / hbm_peak, 4),

@@ -19,6 +19,9 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 #define STAMP(k) do { if (p.dbg && tid == 0) p.dbg[(long long)blockIdx.x * 16 + (k)] = gtime(); } while (0)
 
 __device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16(x)); }
+// two roundings with ONE conversion instruction (F2FP packs a pair; it issues at the special-function rate, so a prologue made of
+// single-value roundings is bound by it)
+__device__ __forceinline__ void rbf2(float& a, float& b) { const float2 r = br::unpack_bf16(br::pack_bf16(a, b)); a = r.x; b = r.y; }
 
 struct FusedParams {
     const bf16* qkv; long long ld;        // raw (pre-norm, pre-rope) fused QKV of the new tokens [R, ld]
@@ -78,10 +81,15 @@ __device__ __forceinline__ void norm_rope_q8_pre(float (&lo)[8], float (&hi)[8],
     const float rstd = rsqrtf(ss / (float)D + eps);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const float a = rbf(wl[e] * rbf(lo[e] * rstd)), b = rbf(wh[e] * rbf(hi[e] * rstd));
+        float a = lo[e] * rstd, b = hi[e] * rstd;
+        rbf2(a, b);
+        a *= wl[e]; b *= wh[e];
+        rbf2(a, b);
         const float cs = cs_sn[e].x, sn = cs_sn[e].y;
-        lo[e] = rbf(a * cs) + rbf(-b * sn);
-        hi[e] = rbf(b * cs) + rbf(a * sn);
+        float ac = a * cs, bs = -b * sn, bc = b * cs, as = a * sn;
+        rbf2(ac, bs); rbf2(bc, as);
+        lo[e] = ac + bs;
+        hi[e] = bc + as;
     }
 }
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
@@ -200,13 +208,15 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p, c
     }
     float wl[8], wh[8];
     { uint4 a = __ldg(reinterpret_cast<const uint4*>(p.qw + sub * 8)), b = __ldg(reinterpret_cast<const uint4*>(p.qw + 64 + sub * 8)); unpack8(a, wl); unpack8(b, wh); }
-    auto load_pairs = [&](int pos, float2 (&t)[8]) {
-        const float4* tp = reinterpret_cast<const float4*>(p.rope + (long long)(pos < 0 ? 0 : pos) * (D / 2) + sub * 8);
+    // rope pairs of ALL four passes, requested here (before the dependency wait) and kept packed (the table holds bf16-rounded cos / sin,
+    // so bf16x2 words lose nothing): a pass that fetched its pairs itself could not be shorter than an L2 round trip
+    uint32_t tcp[4][8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { const float4 t4 = __ldg(tp + e); t[2 * e] = make_float2(t4.x, t4.y); t[2 * e + 1] = make_float2(t4.z, t4.w); }
-    };
-    float2 tcs[8];
-    load_pairs(posv[0], tcs);
+    for (int i = 0; i < 4; ++i) {
+        const float4* tp = reinterpret_cast<const float4*>(p.rope + (long long)(posv[i] < 0 ? 0 : posv[i]) * (D / 2) + sub * 8);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float4 t4 = __ldg(tp + e); tcp[i][2 * e] = br::pack_bf16(t4.x, t4.y); tcp[i][2 * e + 1] = br::pack_bf16(t4.z, t4.w); }
+    }
     // new-token K: norm weight + rope pair of the lane's two dims (owner item, warp 0)
     float2 kcs[E]; float kwl[E], kwh[E];
     if (owns_newest && warp == 0) {
@@ -240,35 +250,26 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p, c
             else if (lane < D / 8) vraw = __ldcg(reinterpret_cast<const uint4*>(p.qkv + (long long)row_base * p.ld + (long long)(p.Hq + p.Hkv + kvh) * D) + lane);
         }
         STAMP(8);
-        // raw chunks -> their final (swizzled) place in the Q tile; each lane re-reads only what it wrote
+        // ---- queries: norm + rope (slot s -> row s / GQ, head kvh*GQ + s % GQ); 8 lanes per vector, 4 vectors per warp per pass, straight
+        // from the registers the raw chunks landed in to their final (swizzled) place in the Q tile.  Slots are ordered by row: the passes
+        // that hold a live query vector form a prefix (private items: ONE pass of warp 0, none of warp 1); dead slots get zeros.
+        const int live_slots = min(rows_per_unit, max(p.R - row_base, 0)) * p.GQ - warp * 16;
+        const int n_pass = live_slots <= 0 ? 0 : min(4, (live_slots + 3) >> 2);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int s = warp * 16 + i * 4 + q4;
-            *reinterpret_cast<uint4*>(qptr(s, sub)) = rl[i];
-            *reinterpret_cast<uint4*>(qptr(s, 8 + sub)) = rh[i];
-        }
-        // ---- queries: norm + rope in place (slot s -> row s / GQ, head kvh*GQ + s % GQ); 8 lanes per vector, 4 vectors per warp per pass
-#pragma unroll 1
-        for (int i = 0; i < 4; ++i) {
-            const int s = warp * 16 + i * 4 + q4;
-            const int pos = i == 0 ? posv[0] : (i == 1 ? posv[1] : (i == 2 ? posv[2] : posv[3]));
-            const int pos_n = i == 0 ? posv[1] : (i == 1 ? posv[2] : posv[3]);
-            float2 nxt[8];
-            if (i < 3) load_pairs(pos_n, nxt);                         // next pass's rope pairs in flight during this pass
-            float lo[8], hi[8];
-            unpack8(*reinterpret_cast<const uint4*>(qptr(s, sub)), lo);
-            unpack8(*reinterpret_cast<const uint4*>(qptr(s, 8 + sub)), hi);
-            norm_rope_q8_pre<D>(lo, hi, wl, wh, tcs, p.eps);
-            if (pos < 0) {
+            uint4 olo = make_uint4(0, 0, 0, 0), ohi = olo;
+            if (i < n_pass) {                                          // warp-uniform
+                float lo[8], hi[8];
+                float2 cs[8];
+                unpack8(rl[i], lo); unpack8(rh[i], hi);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) lo[e] = hi[e] = 0.f;
+                for (int e = 0; e < 8; ++e) cs[e] = br::unpack_bf16(tcp[i][e]);
+                norm_rope_q8_pre<D>(lo, hi, wl, wh, cs, p.eps);
+                if (posv[i] >= 0) { olo = pack8(lo); ohi = pack8(hi); }
             }
-            *reinterpret_cast<uint4*>(qptr(s, sub)) = pack8(lo);
-            *reinterpret_cast<uint4*>(qptr(s, 8 + sub)) = pack8(hi);
-            if (i < 3) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) tcs[e] = nxt[e];
-            }
+            *reinterpret_cast<uint4*>(qptr(s, sub)) = olo;
+            *reinterpret_cast<uint4*>(qptr(s, 8 + sub)) = ohi;
         }
         STAMP(9);
         // ---- append the new token's K / V (private item that owns the newest page)
@@ -553,34 +554,40 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p, c
     __syncthreads();
     STAMP(6);
     {
-        float* s_w = reinterpret_cast<float*>(smem);                   // [GQ][32] slot weights (tile smem is free now)
+        // Every thread owns one float4 column of one head: it loads the head's slot LSEs itself (the same addresses across the threads
+        // of a head: broadcast) together with its column of every slot -- ONE L2 round trip -- and derives the slot weights redundantly
+        // in a fixed order (n_slots <= 32 exponentials per thread are cheaper than a second dependent trip through shared memory).
         const int row = row_base;
         const int per_row = p.GQ * (D / 4);                            // float4 chunks of this (row, kv head) output
         const int lo = (per_row * split) / p.SP, hi = (per_row * (split + 1)) / p.SP;
-        // slot weights of the heads this share touches: softmax over the slots' LSEs (one coalesced load per head, warp reductions)
-        for (int hl = lo / (D / 4) + warp; hl <= (hi - 1) / (D / 4) && hi > lo; hl += 2) {
-            const float* lse = p.part_lse + ((long long)row * p.Hq + kvh * p.GQ + hl) * p.n_slots;
-            const float l = lane < p.n_slots ? __ldcg(lse + lane) : -INFINITY;
-            const float mx = br::warp_max(l);
-            const float e = (l == -INFINITY) ? 0.f : __expf(l - mx);
-            const float den = br::warp_sum(e);
-            s_w[hl * 32 + lane] = den > 0.f ? e / den : 0.f;
-        }
-        __syncthreads();
         for (int idx = lo + tid; idx < hi; idx += NT) {
             const int hl = idx / (D / 4), d0 = (idx % (D / 4)) * 4;
-            const float* po = p.part_o + ((long long)row * p.Hq + kvh * p.GQ + hl) * p.n_slots * D + d0;
+            const long long hb = ((long long)row * p.Hq + kvh * p.GQ + hl) * p.n_slots;
+            const float* po = p.part_o + hb * D + d0;
+            float ls[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ls[j] = j < p.n_slots ? __ldcg(p.part_lse + hb + j) : -INFINITY;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            float mx = -INFINITY, den = 0.f;
+            bool have_w = false;
 #pragma unroll 1
-            for (int s0 = 0; s0 < p.n_slots; s0 += 16) {
-                float4 va[16];
+            for (int s0 = 0; s0 < p.n_slots; s0 += 24) {
+                float4 va[24];
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
+                for (int j = 0; j < 24; ++j)
                     va[j] = (s0 + j < p.n_slots) ? __ldcg(reinterpret_cast<const float4*>(po + (long long)(s0 + j) * D)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!have_w) {                                         // slot weights: softmax over the slots' LSEs, fixed order
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {                         // fixed slot order: deterministic
-                    const float w = (s0 + j < p.n_slots) ? s_w[hl * 32 + s0 + j] : 0.f;
-                    acc.x += w * va[j].x; acc.y += w * va[j].y; acc.z += w * va[j].z; acc.w += w * va[j].w;
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, ls[j]);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { ls[j] = (ls[j] == -INFINITY) ? 0.f : __expf(ls[j] - mx); den += ls[j]; }
+                    den = den > 0.f ? 1.f / den : 0.f;
+                    have_w = true;
+                }
+#pragma unroll
+                for (int j = 0; j < 24; ++j) {                         // fixed slot order: deterministic
+                    const float w = (s0 == 0 ? ls[j] : ls[(24 + j) & 31]) * den;     // second batch: slots 24..31
+                    if (s0 + j < p.n_slots) { acc.x += w * va[j].x; acc.y += w * va[j].y; acc.z += w * va[j].z; acc.w += w * va[j].w; }
                 }
             }
             *reinterpret_cast<uint2*>(p.out + (long long)row * p.ldo + (long long)(kvh * p.GQ + hl) * D + d0) =

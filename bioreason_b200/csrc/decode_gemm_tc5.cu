@@ -179,6 +179,7 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const int u_hi = min(p.units, u_lo + p.chunk);
 
     br::launch_dependents();
+    SKSTAMP(0);
     if (warp == 0 && lane == 0) {
         br::tma_prefetch_desc(&tmW);
         br::tma_prefetch_desc(&tmX);
@@ -256,11 +257,10 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     } else {
         const int lane_grp = warp & 3;
         const int et = threadIdx.x - 64;                      // 0..127 within the epilogue group
-        SKSTAMP(0);
+        SKSTAMP(2);                                           // TMEM allocated, barriers initialised
         br::grid_dep_wait();                                  // everything below touches data shared with earlier kernels
         SKSTAMP(1);
         compute_row_rstd(p, et, s_rs, s_rs + 32);
-        SKSTAMP(2);
         int as = 0; uint32_t aph = 0;
         int u = u_lo;
         while (u < u_hi) {
@@ -674,7 +674,7 @@ int br_skinny_gemm_pf(const void* X, int64_t ldx, const void* W, int64_t ldw, vo
 
 
 /* profiling aid: [n_launches, 160, 8] int64 %globaltimer stamps of the next br_skinny_gemm launches (NULL disables):
- * 0 start, 1 dependency wait passed, 2 row statistics ready, 3 first accumulator, 4 last partial published, 5 reduction loads done,
+ * 0 kernel entry, 1 dependency wait passed, 2 prologue done (TMEM allocated, barriers initialised), 3 first accumulator, 4 last partial published, 5 reduction loads done,
  * 6 reducer epilogue done, 7 CTA done */
 int br_skinny_debug(long long* buf) { g_sk_dbg = buf; g_sk_dbg_slot = 0; return BR_OK; }
 

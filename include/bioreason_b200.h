@@ -161,7 +161,7 @@ int br_skinny_chain(const br_skinny_phase* phases, int n_phases, int R, float ep
  * tiles done, barrier arrive, barrier pass) written by the next br_skinny_chain launches; NULL disables */
 int br_skinny_chain_debug(long long* buf);
 /* profiling aid for br_skinny_gemm(_ex): [n_launches, 160, 8] int64 %globaltimer stamps per CTA of the following launches
- * (start, dependency wait passed, row statistics, first accumulator, partial published, reduction loads, reducer epilogue, done) */
+ * (kernel entry, dependency wait passed, prologue done, first accumulator, partial published, reduction loads, reducer epilogue, done) */
 int br_skinny_debug(long long* buf);
 int br_embed_gather_sumsq(const int64_t* ids, const void* table, int64_t ldt, int64_t vocab, void* out, int64_t ldo, int M, int d,
                           float* sumsq, void* stream);

@@ -68,7 +68,7 @@ qkv = torch.randn(R, (Hq + 2 * Hkv) * D, device=dev).to(bf)
 qn = torch.ones(D, device=dev).to(bf); kn = torch.ones(D, device=dev).to(bf)
 cur = torch.full((R,), T, dtype=torch.int32, device=dev)
 rope = ops.rope_table(T + 8, D, 1e6, dev)
-for ss, sp in ((8, 2), (16, 2), (8, 4), (4, 1)):
+for ss, sp in ((8, 2), (14, 3), (16, 2), (28, 3), (28, 2), (4, 1)):
     wsf = ops.decode_fused_workspace(R, Hq, Hkv, D, ss + sp, dev)
     out = torch.empty(R, Hq * D, device=dev, dtype=bf)
     us = timed_graph(lambda: ops.decode_attn_fused(qkv, qn, kn, kc, vc, table, cur, G, Hq, Hkv, D, n_shared, ss, sp, 1e6, 1e-6, wsf, out, rope=rope), inner=4)

@@ -47,7 +47,7 @@ lib().br_skinny_debug(ffi.NULL); lib().br_decode_attn_fused_debug(ffi.NULL)
 sk = sk.double().cpu(); at = at.double().cpu()
 li = NL - 1
 t0 = sk[li * 4][:, 0][sk[li * 4][:, 0] > 0].min()
-names = ["start", "dep-pass", "rstd", "first-acc", "published", "red-loads", "red-epi", "done"]
+names = ["entry", "dep-pass", "ready", "first-acc", "published", "red-loads", "red-epi", "done"]
 def stat(col):
     v = col[col > 0]
     return "   -   " if v.numel() == 0 else f"{(v.mean() - t0) / 1e3:5.1f}/{(v.max() - t0) / 1e3:5.1f}"
