@@ -15,6 +15,7 @@ LIB = os.path.join(OUT_DIR, "libbioreason_b200.so")
 NVCC = os.environ.get("NVCC", shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+FLAGS += os.environ.get("BR_NVCC_EXTRA", "").split()          # experiments only (e.g. -DBR_SK_NSTAGE=4); part of the object digests
 
 
 def _nccl_include():

@@ -255,18 +255,28 @@ __global__ void __launch_bounds__(64) decode_fused_kernel(const FusedParams p, c
         // that hold a live query vector form a prefix (private items: ONE pass of warp 0, none of warp 1); dead slots get zeros.
         const int live_slots = min(rows_per_unit, max(p.R - row_base, 0)) * p.GQ - warp * 16;
         const int n_pass = live_slots <= 0 ? 0 : min(4, (live_slots + 3) >> 2);
-#pragma unroll
+        // A real loop (one copy of the arithmetic in the instruction cache: this code runs once per CTA, so straight-line code is bound by
+        // instruction fetch); the pass's operands are picked out of the preloaded registers with selects instead of indexed arrays.
+        auto pick4 = [](int i, const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
+            uint4 r;
+            r.x = i == 0 ? a.x : (i == 1 ? b.x : (i == 2 ? c.x : d.x)); r.y = i == 0 ? a.y : (i == 1 ? b.y : (i == 2 ? c.y : d.y));
+            r.z = i == 0 ? a.z : (i == 1 ? b.z : (i == 2 ? c.z : d.z)); r.w = i == 0 ? a.w : (i == 1 ? b.w : (i == 2 ? c.w : d.w));
+            return r;
+        };
+#pragma unroll 1
         for (int i = 0; i < 4; ++i) {
             const int s = warp * 16 + i * 4 + q4;
             uint4 olo = make_uint4(0, 0, 0, 0), ohi = olo;
             if (i < n_pass) {                                          // warp-uniform
+                const uint4 ql = pick4(i, rl[0], rl[1], rl[2], rl[3]), qh = pick4(i, rh[0], rh[1], rh[2], rh[3]);
+                const int pos = i == 0 ? posv[0] : (i == 1 ? posv[1] : (i == 2 ? posv[2] : posv[3]));
                 float lo[8], hi[8];
                 float2 cs[8];
-                unpack8(rl[i], lo); unpack8(rh[i], hi);
+                unpack8(ql, lo); unpack8(qh, hi);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) cs[e] = br::unpack_bf16(tcp[i][e]);
+                for (int e = 0; e < 8; ++e) cs[e] = br::unpack_bf16(i == 0 ? tcp[0][e] : (i == 1 ? tcp[1][e] : (i == 2 ? tcp[2][e] : tcp[3][e])));
                 norm_rope_q8_pre<D>(lo, hi, wl, wh, cs, p.eps);
-                if (posv[i] >= 0) { olo = pack8(lo); ohi = pack8(hi); }
+                if (pos >= 0) { olo = pack8(lo); ohi = pack8(hi); }
             }
             *reinterpret_cast<uint4*>(qptr(s, sub)) = olo;
             *reinterpret_cast<uint4*>(qptr(s, 8 + sub)) = ohi;

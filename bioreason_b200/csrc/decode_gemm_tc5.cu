@@ -58,7 +58,10 @@ struct SL {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BNX * BK * 2;
     static constexpr int STAGE = A_BYTES + B_BYTES;
-    static constexpr int NSTAGE = 6;        // 108 KB: two CTAs (this kernel + its PDL successor) fit one SM
+#ifndef BR_SK_NSTAGE
+#define BR_SK_NSTAGE 6
+#endif
+    static constexpr int NSTAGE = BR_SK_NSTAGE;   // 6 stages = 108 KB: two CTAs (this kernel + its PDL successor) fit one SM
     static constexpr int TILE_BYTES = NSTAGE * STAGE;
     static constexpr int TOTAL = TILE_BYTES + 1024 + 1024;   // + barriers / flags / per-row rstd + alignment slack
 };
