@@ -194,8 +194,10 @@ class RolloutEngine:
                 self._cached.clear()
             St = SimpleNamespace()
             St.table = table.to(dev)
-            St.kc = torch.empty(nl, n_pages, Hkv, PAGE, D, device=dev, dtype=torch.bfloat16)
-            St.vc = torch.empty_like(St.kc)
+            # zero-filled once: the unwritten slots of a partially filled page are multiplied by exact-zero probabilities in the P V
+            # product, which is only harmless if they hold finite numbers (recycled allocator memory may hold NaN bit patterns)
+            St.kc = torch.zeros(nl, n_pages, Hkv, PAGE, D, device=dev, dtype=torch.bfloat16)
+            St.vc = torch.zeros_like(St.kc)
             St.pp_dev = [p.to(dev) for p in prefill_pages]
         table, kc, vc, pp_dev = St.table, St.kc, St.vc, St.pp_dev
 

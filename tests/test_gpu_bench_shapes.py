@@ -176,7 +176,7 @@ def test_config_c_rollout_prefix_sharing_greedy_and_eos():
     ids_e, st = m.generate(**batch, max_new_tokens=n, do_sample=False, use_graph=False, return_stats=True)
     ids_g = m.generate(**batch, max_new_tokens=n, do_sample=False, use_graph=True)
     assert st["G"] == G and st["unique_prompts"] == 1 and st["n_shared_pages"] == batch["input_ids"].shape[1] // 64 == 28
-    assert torch.equal(ids_e, ids_g), "graph replay and eager decode disagree"
+    assert torch.equal(ids_e, ids_g), f"graph replay and eager decode disagree: eager {ids_e.tolist()} graph {ids_g.tolist()}"
     assert all(torch.equal(ids_e[0], ids_e[r]) for r in range(G)), "rows of one greedy group must be identical"
     flips = _first_mismatch_ok(ids_e.cpu(), want, margins, tol=0.05)
     print(f"(c) greedy V={tc.vocab_size}: ids {ids_e[0].tolist()} oracle {want[0].tolist()} min margin {margins.min():.3f} near-tie flips {flips}")

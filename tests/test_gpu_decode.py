@@ -354,3 +354,21 @@ def test_generate_eos_and_multi_group(golden, tiny_oracle):
     got, st = m.generate(**mix, max_new_tokens=6, do_sample=False, return_stats=True)
     assert st["G"] == 2 and st["unique_prompts"] == 2
     _first_mismatch_ok(got.cpu(), want, margins, tol=0.02)
+
+
+def test_generate_ignores_recycled_allocator_garbage(golden, tiny_oracle):
+    """Buffers of a rollout come from torch's caching allocator, i.e. they may hold anything -- including NaN bit patterns -- that an
+    earlier tensor left behind.  Masked positions are multiplied by exact-zero probabilities, which is only harmless for finite
+    operands: the paged KV cache is zero-filled once, every other buffer is fully written before it is read.  (Found by running the
+    config (c) rollout test after the backward tests in one process: eager and graph rollouts disagreed.)"""
+    from bioreason_b200.models import DNALLMModel
+    D = golden["D"]
+    clean = DNALLMModel.from_oracle(tiny_oracle).generate(**D["batch"], max_new_tokens=12, do_sample=False).cpu()
+    for rep in range(2):
+        junk = [torch.full((n,), float("nan"), device="cuda", dtype=torch.bfloat16) for n in (1 << 18, 1 << 20, 1 << 22, 1 << 24)]
+        junk += [torch.full((n,), float("inf"), device="cuda", dtype=torch.float32) for n in (1 << 18, 1 << 20, 1 << 22)]
+        del junk                                                             # back to the allocator's free lists, contents intact
+        m = DNALLMModel.from_oracle(tiny_oracle)                            # fresh rollout caches -> recycled blocks
+        for use_graph in (False, True):
+            got = m.generate(**D["batch"], max_new_tokens=12, do_sample=False, use_graph=use_graph).cpu()
+            assert torch.equal(got, clean), f"rep {rep} graph={use_graph}"
