@@ -9,6 +9,7 @@
 //                   dP = dO V^T             (SS)
 //                   dS = P o (dP - delta) * scale   one thread per query row (TMEM lane), bf16 into TMEM over dP
 //                   dQ += dS K              (TS: A = dS in TENSOR MEMORY, B = the K tile as it landed, MN-major descriptor)
+//                 three score buffers (all 512 TMEM columns): S / dP of tile t + 2 are issued while tiles t, t + 1 are in the two groups;
 //                 also computes delta = rowsum(dO o O) for its rows and publishes it for the dk/dv kernel.
 //   dk/dv kernel: CTA = 128-key tile of one (row, kv head); loops over the query heads of the group and the 64-query tiles that
 //                 can see the keys; dK and dV accumulate in TMEM for the whole loop.
@@ -19,7 +20,7 @@
 // tensor pipe computes the scores of tile t+1 while tile t is in its exp2 stage and the two groups sit in different phases of the
 // chain (scores ready -> tcgen05.ld -> exp2 -> tcgen05.st -> operand ready).  The first tcgen05 version used one score buffer and
 // 256 threads in lock-step on 128-wide tiles: tensor pipe idle during the whole element-wise stage, 30 % / 32 % active under ncu.
-// TMEM: 384 / 512 columns; one CTA per SM (~162 KB of shared memory: two resident tiles + 3-stage rings of the two streamed tiles).
+// TMEM: 512 / 512 columns; one CTA per SM (~180 / 162 KB of shared memory: two resident tiles + 3- or 4-stage rings of the two streamed tiles).
 #include "br_common.cuh"
 #include "../../include/bioreason_b200.h"
 
@@ -79,7 +80,8 @@ __device__ __forceinline__ void store_row_bf16(bf16* dst, const uint32_t (&r)[32
 // =====================================================================================================================
 // dq kernel
 // =====================================================================================================================
-constexpr int DQ_OFF_Q = 0, DQ_OFF_DO = TILE, DQ_OFF_K = 2 * TILE, DQ_OFF_V = DQ_OFF_K + NST * TILES, DQ_OFF_RED = DQ_OFF_V + NST * TILES,
+constexpr int NSTK = 4;                   // dq kernel: a K tile is held until dQ += dS K of ITS tile retires (two tiles after its scores) -> one more stage
+constexpr int DQ_OFF_Q = 0, DQ_OFF_DO = TILE, DQ_OFF_K = 2 * TILE, DQ_OFF_V = DQ_OFF_K + NSTK * TILES, DQ_OFF_RED = DQ_OFF_V + NST * TILES,
               DQ_OFF_BAR = DQ_OFF_RED + 256 * 4;
 constexpr int DQ_SMEM = DQ_OFF_BAR + 256 + 1024;
 
@@ -91,13 +93,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     float* s_red = reinterpret_cast<float*>(smem + DQ_OFF_RED);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_OFF_BAR);
     uint64_t* qdo_full = bars;                    // 1
-    uint64_t* k_full = bars + 1;                  // NST
-    uint64_t* v_full = k_full + NST;
-    uint64_t* k_empty = v_full + NST;
-    uint64_t* v_empty = k_empty + NST;
-    uint64_t* sdp_full = v_empty + NST;           // 2: S and dP of tile t (buffer t & 1) ready
-    uint64_t* ds_full = sdp_full + 2;             // 2: dS of tile t in TMEM
-    uint64_t* dq_final = ds_full + 2;
+    uint64_t* k_full = bars + 1;                  // NSTK
+    uint64_t* v_full = k_full + NSTK;             // NST
+    uint64_t* k_empty = v_full + NST;             // NSTK
+    uint64_t* v_empty = k_empty + NSTK;           // NST
+    uint64_t* sdp_full = v_empty + NST;           // 3: S and dP of tile t (buffer t % 3) ready
+    uint64_t* ds_full = sdp_full + 3;             // 3: dS of tile t in TMEM
+    uint64_t* dq_final = ds_full + 3;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_final + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -116,8 +118,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (warp == 0 && lane == 0) {
         br::tma_prefetch_desc(&tmQ); br::tma_prefetch_desc(&tmK); br::tma_prefetch_desc(&tmV); br::tma_prefetch_desc(&tmDO);
         br::mbar_init(qdo_full, 1);
-        for (int s = 0; s < NST; ++s) { br::mbar_init(&k_full[s], 1); br::mbar_init(&v_full[s], 1); br::mbar_init(&k_empty[s], 1); br::mbar_init(&v_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { br::mbar_init(&sdp_full[s], 1); br::mbar_init(&ds_full[s], 4); }
+        for (int s = 0; s < NSTK; ++s) { br::mbar_init(&k_full[s], 1); br::mbar_init(&k_empty[s], 1); }
+        for (int s = 0; s < NST; ++s) { br::mbar_init(&v_full[s], 1); br::mbar_init(&v_empty[s], 1); }
+        for (int s = 0; s < 3; ++s) { br::mbar_init(&sdp_full[s], 1); br::mbar_init(&ds_full[s], 4); }
         br::mbar_init(dq_final, 1);
         br::mbar_fence_init();
     }
@@ -126,7 +129,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncthreads();
     br::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 2 * BS, tm_dq = tmem_base + 4 * BS;     // S[2], dP[2] (64 columns each), dQ (128)
+    // S[3], dP[3] (64 columns each), dQ (128): THREE score buffers for two element-wise groups, so the scores of the tile a group
+    // turns to next were issued a whole tile period earlier (with two buffers they could only be issued once that group had released
+    // its buffer, and every tile began with a wait for the tensor pipe)
+    const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 3 * BS, tm_dq = tmem_base + 6 * BS;
 
     if (warp == 0) {
         if (lane == 0 && n_tiles > 0) {
@@ -134,16 +140,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             br::mbar_expect_tx(qdo_full, 2 * TILE);
             tma_tile(smem + DQ_OFF_Q, &tmQ, qdo_full, h * D, row_q, BLK);
             tma_tile(smem + DQ_OFF_DO, &tmDO, qdo_full, h * D, row_q, BLK);
-            int s = 0; uint32_t ph = 0;
+            int sk = 0, sv = 0; uint32_t phk = 0, phv = 0;
             for (int t = 0; t < n_tiles; ++t) {
                 const int row_k = b * p.L + (jb_lo + t) * BS;
-                br::mbar_wait(&k_empty[s], ph ^ 1);
-                br::mbar_expect_tx(&k_full[s], TILES);
-                tma_tile(smem + DQ_OFF_K + s * TILES, &tmK, &k_full[s], hk * D, row_k, BLKS);
-                br::mbar_wait(&v_empty[s], ph ^ 1);
-                br::mbar_expect_tx(&v_full[s], TILES);
-                tma_tile(smem + DQ_OFF_V + s * TILES, &tmV, &v_full[s], hk * D, row_k, BLKS);
-                if (++s == NST) { s = 0; ph ^= 1; }
+                br::mbar_wait(&k_empty[sk], phk ^ 1);
+                br::mbar_expect_tx(&k_full[sk], TILES);
+                tma_tile(smem + DQ_OFF_K + sk * TILES, &tmK, &k_full[sk], hk * D, row_k, BLKS);
+                br::mbar_wait(&v_empty[sv], phv ^ 1);
+                br::mbar_expect_tx(&v_full[sv], TILES);
+                tma_tile(smem + DQ_OFF_V + sv * TILES, &tmV, &v_full[sv], hk * D, row_k, BLKS);
+                if (++sk == NSTK) { sk = 0; phk ^= 1; }
+                if (++sv == NST) { sv = 0; phv ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -151,28 +158,30 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const uint32_t q_addr = br::smem_u32(smem + DQ_OFF_Q), do_addr = br::smem_u32(smem + DQ_OFF_DO);
             br::mbar_wait(qdo_full, 0);
             br::tc_fence_after();
-            int s = 0; uint32_t ph = 0;          // ring position of tile t
-            int su = 0;                          // ring position of tile t - 1
-            for (int t = 0; t <= n_tiles; ++t) {
+            int sk = 0, sv = 0; uint32_t phk = 0, phv = 0;   // ring positions of tile t
+            int su = 0;                                      // K ring position of tile t - 2
+            for (int t = 0; t < n_tiles + 2; ++t) {
                 if (t < n_tiles) {
-                    const uint32_t k_addr = br::smem_u32(smem + DQ_OFF_K + s * TILES), v_addr = br::smem_u32(smem + DQ_OFF_V + s * TILES);
-                    br::mbar_wait(&k_full[s], ph);
+                    const uint32_t k_addr = br::smem_u32(smem + DQ_OFF_K + sk * TILES), v_addr = br::smem_u32(smem + DQ_OFF_V + sv * TILES);
+                    const int b3 = t % 3;
+                    br::mbar_wait(&k_full[sk], phk);
                     br::tc_fence_after();
-                    mma_ss_kmajor(tm_s + (t & 1) * BS, q_addr, k_addr);                     // S = Q K^T
-                    br::mbar_wait(&v_full[s], ph);
+                    mma_ss_kmajor(tm_s + b3 * BS, q_addr, k_addr);                          // S = Q K^T
+                    br::mbar_wait(&v_full[sv], phv);
                     br::tc_fence_after();
-                    mma_ss_kmajor(tm_dp + (t & 1) * BS, do_addr, v_addr);                   // dP = dO V^T
-                    br::tc_commit(&sdp_full[t & 1]);
-                    br::tc_commit(&v_empty[s]);
-                    if (++s == NST) { s = 0; ph ^= 1; }
+                    mma_ss_kmajor(tm_dp + b3 * BS, do_addr, v_addr);                        // dP = dO V^T
+                    br::tc_commit(&sdp_full[b3]);
+                    br::tc_commit(&v_empty[sv]);
+                    if (++sk == NSTK) { sk = 0; phk ^= 1; }
+                    if (++sv == NST) { sv = 0; phv ^= 1; }
                 }
-                if (t >= 1) {
-                    const int u = t - 1;
-                    br::mbar_wait(&ds_full[u & 1], (u >> 1) & 1);
+                if (t >= 2) {
+                    const int u = t - 2, b3 = u % 3;
+                    br::mbar_wait(&ds_full[b3], (u / 3) & 1);
                     br::tc_fence_after();
-                    mma_ts_mnmajor(tm_dq, tm_dp + (u & 1) * BS, br::smem_u32(smem + DQ_OFF_K + su * TILES), u != 0);     // dQ += dS K
+                    mma_ts_mnmajor(tm_dq, tm_dp + b3 * BS, br::smem_u32(smem + DQ_OFF_K + su * TILES), u != 0);          // dQ += dS K
                     br::tc_commit(&k_empty[su]);
-                    if (++su == NST) su = 0;
+                    if (++su == NSTK) su = 0;
                 }
             }
             br::tc_commit(dq_final);
@@ -208,8 +217,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int t = g; t < n_tiles; t += 2) {
             const int k0 = (jb_lo + t) * BS;
             const bool need_mask = (k0 < ks) || (k0 + BS > ke) || (k0 + BS - 1 > q0);
-            const uint32_t ts = tm_s + g * BS + lane_off, tp = tm_dp + g * BS + lane_off;
-            br::mbar_wait(&sdp_full[g], (t >> 1) & 1);
+            const int b3 = t % 3;
+            const uint32_t ts = tm_s + b3 * BS + lane_off, tp = tm_dp + b3 * BS + lane_off;
+            br::mbar_wait(&sdp_full[b3], (t / 3) & 1);
             br::tc_fence_after();
 #pragma unroll
             for (int c = 0; c < BS; c += 32) {
@@ -218,14 +228,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 br::tmem_ld_32x32(tp + c, rp);
                 br::tmem_ld_wait();
                 uint32_t pk[16];
+                if (need_mask) {                                         // one branch per chunk: the arithmetic below stays one basic block
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const int j = k0 + c + e;
+                        if (!((j >= ks) && (j < ke) && (j <= i_glob))) rs[e] = 0xff800000u;      // -inf score -> probability 0
+                    }
+                }
 #pragma unroll
                 for (int e = 0; e < 32; e += 2) {
-                    float x0 = fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse2), x1 = fmaf(__uint_as_float(rs[e + 1]), p.scale_log2, -lse2);
-                    if (need_mask) {
-                        const int j = k0 + c + e;
-                        x0 = ((j >= ks) && (j < ke) && (j <= i_glob)) ? x0 : -INFINITY;
-                        x1 = ((j + 1 >= ks) && (j + 1 < ke) && (j + 1 <= i_glob)) ? x1 : -INFINITY;
-                    }
+                    const float x0 = fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse2), x1 = fmaf(__uint_as_float(rs[e + 1]), p.scale_log2, -lse2);
                     const float p0 = ex2(x0), p1 = ex2(x1);
                     const float d0 = p0 * fmaf(__uint_as_float(rp[e]), p.scale, -delta_s), d1 = p1 * fmaf(__uint_as_float(rp[e + 1]), p.scale, -delta_s);
                     pk[e >> 1] = br::pack_bf16(d0, d1);
@@ -235,7 +247,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             br::tmem_st_wait();
             br::tc_fence_before();
             __syncwarp();
-            if (lane == 0) br::mbar_arrive(&ds_full[g]);
+            if (lane == 0) br::mbar_arrive(&ds_full[b3]);
         }
         bf16* dq_row = p.dq + tok * p.lddq + (long long)h * D + col0;
         if (n_tiles > 0) {
@@ -396,6 +408,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 br::tmem_ld_32x32(tp + c, rp);
                 br::tmem_ld_wait();
                 uint32_t pk[16], dk_[16];
+                if (need_mask) {                                         // one branch per chunk: the arithmetic below stays one basic block
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const int i = q0 + c + e;
+                        if (!(key_ok && j_glob <= i)) rs[e] = 0xff800000u;                       // -inf score (i >= L rows carry lse = +inf)
+                    }
+                }
 #pragma unroll
                 for (int e = 0; e < 32; e += 4) {
                     const float4 l4 = *reinterpret_cast<const float4*>(v_l2 + c + e), d4 = *reinterpret_cast<const float4*>(v_ds + c + e);
@@ -403,9 +422,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     float pr[4], dsv[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        float x = fmaf(__uint_as_float(rs[e + u]), p.scale_log2, -ll[u]);
-                        if (need_mask) { const int i = q0 + c + e + u; x = (key_ok && j_glob <= i) ? x : -INFINITY; }   // i >= L rows carry lse = +inf
-                        pr[u] = ex2(x);
+                        pr[u] = ex2(fmaf(__uint_as_float(rs[e + u]), p.scale_log2, -ll[u]));
                         dsv[u] = pr[u] * fmaf(__uint_as_float(rp[e + u]), p.scale, -dd[u]);
                     }
                     pk[e >> 1] = br::pack_bf16(pr[0], pr[1]); pk[(e >> 1) + 1] = br::pack_bf16(pr[2], pr[3]);
