@@ -166,6 +166,11 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
     return d;
 }
 // A operand read from TMEM (lane = row, two consecutive K elements packed per 32-bit column), B from a shared-memory descriptor
+// shared -> tensor memory copy of one K = 16 slice of a 128-row operand tile (128 lanes x 256 bit = 8 columns); `sdesc` is the same
+// matrix descriptor the MMA would use for that slice.  Ordered with tcgen05.mma issued by the same thread; completion via tc_commit.
+__device__ __forceinline__ void tc_cp_128x256b(uint32_t tmem_dst, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_dst), "l"(sdesc) : "memory");
+}
 __device__ __forceinline__ void tc_mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"

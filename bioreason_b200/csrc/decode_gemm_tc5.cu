@@ -53,7 +53,10 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
         : "memory");
 }
 
-template <int BNX>
+// PARK: tensor memory as a second-level weight buffer.  The CTA uses 2 * BNX of the 256 TMEM columns it may take (two CTAs share an SM);
+// the rest holds NPARK weight tiles in the A-operand layout (tcgen05.cp shared -> tensor memory, consumed by the TS form of the MMA), all
+// of them filled BEFORE the dependency on the previous kernel resolves -- on top of the shared-memory ring.
+template <int BNX, bool PARK>
 struct SL {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BNX * BK * 2;
@@ -61,9 +64,12 @@ struct SL {
 #ifndef BR_SK_NSTAGE
 #define BR_SK_NSTAGE 6
 #endif
-    static constexpr int NSTAGE = BR_SK_NSTAGE;   // 6 stages = 108 KB: two CTAs (this kernel + its PDL successor) fit one SM
+    static constexpr int NSTAGE = PARK ? 5 : BR_SK_NSTAGE;   // 6 stages = 108 KB: two CTAs (this kernel + its PDL successor) fit one SM
+    static constexpr int TMEM_COLS = PARK ? 256 : (2 * BNX < 32 ? 32 : 2 * BNX);
+    static constexpr int NPARK = PARK ? (256 - 2 * BNX) / (BK / 2) : 0;      // a 128 x 64 bf16 tile = 32 columns
     static constexpr int TILE_BYTES = NSTAGE * STAGE;
-    static constexpr int TOTAL = TILE_BYTES + 1024 + 1024;   // + barriers / flags / per-row rstd + alignment slack
+    static constexpr int XP_BYTES = NPARK * B_BYTES;          // activation tiles of the parked weight tiles (loaded after the dependency wait)
+    static constexpr int TOTAL = TILE_BYTES + XP_BYTES + 1024 + 1024;   // + barriers / flags / per-row rstd + alignment slack
 };
 
 // residual values of feature f for all live rows, issued as independent L2 loads (one round trip instead of R dependent ones);
@@ -162,18 +168,22 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
 // BNX: UMMA N (rows of X the tensor core sees, zero-filled beyond R); RM: rows the epilogue code is generated for (R <= RM <= BNX).
 // The epilogue runs once per CTA per launch -- straight-line, instruction-fetch-bound code -- so the common R <= 8 decode batch gets its
 // own half-size instantiation.
-template <int BNX, int RM>
+template <int BNX, int RM, bool PARK>
 __global__ void __launch_bounds__(NTHREADS, 1)
 skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmP,
                   const SkParams p) {
-    using L = SL<BNX>;
+    using L = SL<BNX, PARK>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::TILE_BYTES);
+    uint8_t* xp = smem + L::TILE_BYTES;                        // PARK: [NPARK] activation tiles
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::TILE_BYTES + L::XP_BYTES);
     uint64_t* empty_bar = full_bar + L::NSTAGE;
     uint64_t* tfull_bar = empty_bar + L::NSTAGE;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* pfull_bar = tempty_bar + 2;                      // PARK: weight tile of a stage landed (parking phase)
+    uint64_t* pempty_bar = pfull_bar + L::NSTAGE;              // PARK: stage copied to tensor memory
+    uint64_t* xp_bar = pempty_bar + L::NSTAGE;                 // PARK: activation tiles of the parked weight tiles landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xp_bar + 1);
     int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
     float* s_rs = reinterpret_cast<float*>(s_flag + 1);       // [32] per-row rstd of the folded RMSNorm
 
@@ -188,40 +198,71 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         br::tma_prefetch_desc(&tmX);
         for (int s = 0; s < L::NSTAGE; ++s) { br::mbar_init(&full_bar[s], 1); br::mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { br::mbar_init(&tfull_bar[s], 1); br::mbar_init(&tempty_bar[s], 4); }
+        if constexpr (PARK) {
+            for (int s = 0; s < L::NSTAGE; ++s) { br::mbar_init(&pfull_bar[s], 1); br::mbar_init(&pempty_bar[s], 1); }
+            br::mbar_init(xp_bar, 1);
+        }
         br::mbar_fence_init();
     }
     if (warp == 1) {
-        br::tmem_alloc(tmem_slot, 2 * BNX < 32 ? 32 : 2 * BNX);
+        br::tmem_alloc(tmem_slot, L::TMEM_COLS);
         br::tmem_relinquish();
     }
     br::tc_fence_before();
     __syncthreads();
     br::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // the first n_park units of the chunk are parked in tensor memory (they are consumed first: the accumulation order is unchanged),
+    // the ring holds the units after them
+    const int n_units = u_hi - u_lo;
+    const int n_park = PARK ? min(L::NPARK, max(0, n_units - L::NSTAGE)) : 0;
+    const uint32_t tmem_park = tmem_base + 2 * BNX;
 
     if (warp == 0) {
         if (lane == 0) {
             // The weights are constant during the rollout: fill the whole ring with weight tiles BEFORE waiting for the
             // previous kernel (PDL), so the HBM stream of this layer overlaps the tail of the previous kernel.
-            const int n_pre = min(L::NSTAGE, u_hi - u_lo);
+            const int n_pre = min(L::NSTAGE, n_units - n_park);
             const uint64_t pol = br::make_policy_evict_first();
             auto load_w = [&](void* dst, uint64_t* bar, int c0, int c1) {
                 if (p.w_evict_first) br::tma_load_2d_hint(dst, &tmW, bar, c0, c1, pol);
                 else br::tma_load_2d(dst, &tmW, bar, c0, c1);
             };
+            if constexpr (PARK) {
+                for (int i = 0; i < n_park; ++i) {                                   // through the ring into tensor memory (MMA thread copies)
+                    const int u = u_lo + i, tile = u / p.KB, kb = u - tile * p.KB;
+                    const int st = i % L::NSTAGE, use = i / L::NSTAGE;
+                    if (use > 0) br::mbar_wait(&pempty_bar[st], (use - 1) & 1);
+                    br::mbar_expect_tx(&pfull_bar[st], L::A_BYTES);
+                    load_w(smem + st * L::STAGE, &pfull_bar[st], kb * BK, tile * BM);
+                }
+            }
             for (int i = 0; i < n_pre; ++i) {
-                const int u = u_lo + i, tile = u / p.KB, kb = u - tile * p.KB;
+                const int u = u_lo + n_park + i, tile = u / p.KB, kb = u - tile * p.KB;
+                if constexpr (PARK) {                                                // the stage may still hold a tile on its way to tensor memory
+                    const int uses = (n_park - i + L::NSTAGE - 1) / L::NSTAGE;       // parked tiles that went through stage i
+                    if (i < n_park && uses > 0) br::mbar_wait(&pempty_bar[i], (uses - 1) & 1);
+                }
                 br::mbar_expect_tx(&full_bar[i], L::STAGE);
                 load_w(smem + i * L::STAGE, &full_bar[i], kb * BK, tile * BM);
             }
             if (p.pf_on) br::l2_prefetch_issue(&tmP, p.pf, blockIdx.x, gridDim.x);     // a LATER GEMM's tiles -> L2 (HBM is otherwise idle here)
             br::grid_dep_wait();
+            if constexpr (PARK) {
+                if (n_park > 0) {
+                    br::mbar_expect_tx(xp_bar, n_park * L::B_BYTES);
+                    for (int i = 0; i < n_park; ++i) {
+                        const int u = u_lo + i, tile = u / p.KB, kb = u - tile * p.KB;
+                        br::tma_load_2d(xp + i * L::B_BYTES, &tmX, xp_bar, kb * BK, 0);
+                    }
+                }
+            }
             for (int i = 0; i < n_pre; ++i) {
-                const int u = u_lo + i, tile = u / p.KB, kb = u - tile * p.KB;
+                const int u = u_lo + n_park + i, tile = u / p.KB, kb = u - tile * p.KB;
                 br::tma_load_2d(smem + i * L::STAGE + L::A_BYTES, &tmX, &full_bar[i], kb * BK, 0);
             }
             int s = n_pre % L::NSTAGE; uint32_t ph = (n_pre == L::NSTAGE) ? 1u : 0u;
-            for (int u = u_lo + n_pre; u < u_hi; ++u) {
+            for (int u = u_lo + n_park + n_pre; u < u_hi; ++u) {
                 const int tile = u / p.KB, kb = u - tile * p.KB;
                 br::mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* sa = smem + s * L::STAGE;
@@ -234,8 +275,20 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = br::make_idesc_bf16(BM, BNX);
+            if constexpr (PARK) {
+                for (int i = 0; i < n_park; ++i) {                                   // parking phase (before the dependency resolves)
+                    const int st = i % L::NSTAGE, use = i / L::NSTAGE;
+                    br::mbar_wait(&pfull_bar[st], use & 1);
+                    br::tc_fence_after();
+                    const uint64_t adesc = br::make_sw128_kmajor_desc(br::smem_u32(smem + st * L::STAGE));
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) br::tc_cp_128x256b(tmem_park + i * (BK / 2) + k * 8, adesc + 2 * k);
+                    br::tc_commit(&pempty_bar[st]);
+                }
+            }
             int s = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0;
             int u = u_lo;
+            bool xp_ready = false;
             while (u < u_hi) {
                 const int tile = u / p.KB;
                 const int seg_end = min(u_hi, (tile + 1) * p.KB);
@@ -243,6 +296,17 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 br::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * BNX;
                 for (int i = 0; u < seg_end; ++u, ++i) {
+                    if constexpr (PARK) {
+                        if (u - u_lo < n_park) {                                     // weight tile in tensor memory, activation tile in xp
+                            if (!xp_ready) { br::mbar_wait(xp_bar, 0); br::tc_fence_after(); xp_ready = true; }
+                            const int j = u - u_lo;
+                            const uint64_t bdesc = br::make_sw128_kmajor_desc(br::smem_u32(xp + j * L::B_BYTES));
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k)
+                                br::tc_mma_bf16_ts(tmem_d, tmem_park + j * (BK / 2) + k * 8, bdesc + 2 * k, idesc, (i | k) != 0);
+                            continue;
+                        }
+                    }
                     br::mbar_wait(&full_bar[s], ph);
                     br::tc_fence_after();
                     const uint32_t sa = br::smem_u32(smem + s * L::STAGE);
@@ -358,14 +422,14 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     __syncthreads();
     if (warp == 1) {
         br::tc_fence_after();
-        br::tmem_dealloc(tmem_base, 2 * BNX < 32 ? 32 : 2 * BNX);
+        br::tmem_dealloc(tmem_base, L::TMEM_COLS);
     }
 }
 
-template <int BNX, int RM>
+template <int BNX, int RM, bool PARK>
 int launch(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& tp, const SkParams& p, int grid, cudaStream_t st) {
-    using L = SL<BNX>;
-    auto kern = skinny_tc5_kernel<BNX, RM>;
+    using L = SL<BNX, PARK>;
+    auto kern = skinny_tc5_kernel<BNX, RM, PARK>;
     static bool done = false;
     if (!done) {
         BR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -393,7 +457,7 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 
 template <int BNX>
 __global__ void __launch_bounds__(CHAIN_THREADS, 1) skinny_chain_kernel(const __grid_constant__ ChainParams cp) {
-    using L = SL<BNX>;
+    using L = SL<BNX, false>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::TILE_BYTES);
@@ -599,7 +663,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) skinny_chain_kernel(const __
 
 template <int BNX>
 int launch_chain(const ChainParams& cp, int grid, cudaStream_t st) {
-    using L = SL<BNX>;
+    using L = SL<BNX, false>;
     auto kern = skinny_chain_kernel<BNX>;
     static bool done = false;
     if (!done) { BR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL)); done = true; }
@@ -671,8 +735,14 @@ int br_skinny_gemm_pf(const void* X, int64_t ldx, const void* W, int64_t ldw, vo
         p.pf_on = 1;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (R <= 8) return launch<16, 8>(tw, tx, tp, p, grid, st);
-    return BNX == 16 ? launch<16, 16>(tw, tx, tp, p, grid, st) : launch<32, 32>(tw, tx, tp, p, grid, st);
+    // BR_SKINNY_PARK=1: also buffer weight tiles in tensor memory before the dependency resolves (A/B switch until it is the measured default)
+    static const bool park = getenv("BR_SKINNY_PARK") && atoi(getenv("BR_SKINNY_PARK")) != 0;
+    if (park) {
+        if (R <= 8) return launch<16, 8, true>(tw, tx, tp, p, grid, st);
+        return BNX == 16 ? launch<16, 16, true>(tw, tx, tp, p, grid, st) : launch<32, 32, true>(tw, tx, tp, p, grid, st);
+    }
+    if (R <= 8) return launch<16, 8, false>(tw, tx, tp, p, grid, st);
+    return BNX == 16 ? launch<16, 16, false>(tw, tx, tp, p, grid, st) : launch<32, 32, false>(tw, tx, tp, p, grid, st);
 }
 
 
