@@ -38,6 +38,7 @@ struct SkParams {
     const float* sumsq_in; int sumsq_in_n; float* sumsq_out; float eps;
     long long* dbg; int dbg_slot;       // optional %globaltimer stamps [slot][cta][8] (profiling aid)
     br::L2Prefetch pf; int pf_on;       // L2 staging of a later GEMM's weights (see br_common.cuh)
+    int* gate_counter; const int* gate_epoch; int gate_base, gate_per_step, gate_wait, gate_signal;   // stream gate (see br_stream_gate)
     int w_evict_first;                  // weight tiles are read once per token step: mark them evict-first in L2 so the small
                                         // latency-critical buffers (activations, partial tiles, statistics, tables) stay resident
 };
@@ -224,6 +225,14 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             // previous kernel (PDL), so the HBM stream of this layer overlaps the tail of the previous kernel.
             const int n_pre = min(L::NSTAGE, n_units - n_park);
             const uint64_t pol = br::make_policy_evict_first();
+            if (p.gate_counter && p.gate_wait >= 0) {             // start the early loads under the previous GEMM's exchange tail, not under its stream
+                const int target = (__ldcg(p.gate_epoch) - p.gate_base) * p.gate_per_step + p.gate_wait;
+                for (int it = 0; it < 32; ++it) {                 // bounded: the gate is a timing hint
+                    int seen;
+                    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.gate_counter) : "memory");
+                    if (seen >= target) break;
+                }
+            }
             auto load_w = [&](void* dst, uint64_t* bar, int c0, int c1) {
                 if (p.w_evict_first) br::tma_load_2d_hint(dst, &tmW, bar, c0, c1, pol);
                 else br::tma_load_2d(dst, &tmW, bar, c0, c1);
@@ -308,6 +317,8 @@ skinny_tc5_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                         }
                     }
                     br::mbar_wait(&full_bar[s], ph);
+                    if (u == u_hi - 1 && p.gate_counter && p.gate_signal)          // every weight tile of this CTA is on chip
+                        asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(p.gate_counter) : "memory");
                     br::tc_fence_after();
                     const uint32_t sa = br::smem_u32(smem + s * L::STAGE);
                     const uint64_t adesc = br::make_sw128_kmajor_desc(sa);
@@ -705,9 +716,22 @@ int br_skinny_gemm_ex(const void* X, int64_t ldx, const void* W, int64_t ldw, vo
     return br_skinny_gemm_pf(X, ldx, W, ldw, out, ldo, R, N, K, mode, residual, ldr, scratch, sumsq_in, sumsq_in_n, sumsq_out, eps, nullptr, stream);
 }
 
+int br_skinny_grid(int N, int K) {
+    const int units = ((N + BM - 1) / BM) * ((K + BK - 1) / BK);
+    int grid = units < br_num_sms() ? units : br_num_sms();
+    const int chunk = (units + grid - 1) / grid;
+    return (units + chunk - 1) / chunk;
+}
+
 int br_skinny_gemm_pf(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
                       const void* residual, int64_t ldr, void* scratch, const float* sumsq_in, int sumsq_in_n, float* sumsq_out, float eps,
                       const br_l2_prefetch* prefetch, void* stream) {
+    return br_skinny_gemm_gated(X, ldx, W, ldw, out, ldo, R, N, K, mode, residual, ldr, scratch, sumsq_in, sumsq_in_n, sumsq_out, eps, prefetch, nullptr, stream);
+}
+
+int br_skinny_gemm_gated(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
+                         const void* residual, int64_t ldr, void* scratch, const float* sumsq_in, int sumsq_in_n, float* sumsq_out, float eps,
+                         const br_l2_prefetch* prefetch, const br_stream_gate* gate, void* stream) {
     BR_CHECK_ARG(R >= 1 && R <= 32, "skinny_gemm: R=%d must be in [1, 32]", R);
     BR_CHECK_ARG(N % 16 == 0 && K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "skinny_gemm: N %% 16, K %% 8, ld %% 8 (N=%d K=%d)", N, K);
     BR_CHECK_ARG(mode >= 0 && mode <= 3 && !(mode == 1 && !residual), "skinny_gemm: bad mode %d", mode);
@@ -718,6 +742,12 @@ int br_skinny_gemm_pf(const void* X, int64_t ldx, const void* W, int64_t ldw, vo
     p.sumsq_in = sumsq_in; p.sumsq_in_n = sumsq_in_n; p.sumsq_out = sumsq_out; p.eps = eps;
     BR_CHECK_ARG(!(sumsq_out && mode >= 2), "skinny_gemm: sumsq_out only with bf16 outputs (mode 0/1)");
     p.dbg = g_sk_dbg; p.dbg_slot = g_sk_dbg ? g_sk_dbg_slot++ : 0;
+    p.gate_counter = nullptr; p.gate_epoch = nullptr; p.gate_base = p.gate_per_step = p.gate_signal = 0; p.gate_wait = -1;
+    if (gate && gate->counter) {
+        BR_CHECK_ARG(gate->epoch != nullptr && gate->per_step >= 0, "skinny_gemm: stream gate needs the epoch counter");
+        p.gate_counter = gate->counter; p.gate_epoch = gate->epoch; p.gate_base = gate->epoch_base; p.gate_per_step = gate->per_step;
+        p.gate_wait = gate->wait_prefix; p.gate_signal = gate->signal;
+    }
     { const char* e = getenv("BR_SKINNY_EVICT_FIRST"); p.w_evict_first = e ? atoi(e) : 1; }
     p.tiles_n = (N + BM - 1) / BM; p.KB = (K + BK - 1) / BK; p.units = p.tiles_n * p.KB;
     int grid = p.units < br_num_sms() ? p.units : br_num_sms();

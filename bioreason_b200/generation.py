@@ -185,7 +185,7 @@ class RolloutEngine:
         # Static buffers + the captured decode graph are cached per rollout shape: a training run replays the same graph every
         # step (no per-step capture, no graph-pool / allocator churn -- that churn showed up as multi-second host stalls).
         key = (B, G, tuple(plen), C, n_shared, max_pages, n_pages, params.do_sample, params.temperature, params.top_k, params.top_p,
-               params.eos_token_id, params.pad_token_id, id(Wd), bool(use_graph), os.environ.get("BR_DECODE_CHAIN", "0"), os.environ.get("BR_L2PF", "0"),
+               params.eos_token_id, params.pad_token_id, id(Wd), bool(use_graph), os.environ.get("BR_DECODE_CHAIN", "0"), os.environ.get("BR_L2PF", "0"), os.environ.get("BR_STREAM_GATE", "0"),
                os.environ.get("BR_ATTN_SS", ""), os.environ.get("BR_ATTN_SP", ""))
         St = self._cached.get(key)
         hit = St is not None
@@ -256,8 +256,10 @@ class RolloutEngine:
             St.ssq_b = torch.zeros(n_part_, 32, device=dev, dtype=torch.float32)    # ... entering the MLP (see br_skinny_gemm_ex)
             St.ssq_e = torch.zeros(1, 32, device=dev, dtype=torch.float32)          # ... of the embedding row (first layer)
             St.samp_ws = ops.sample_workspace(R, cfg.vocab_size, dev)
+            St.gate = torch.zeros(1, device=dev, dtype=torch.int32)                  # stream-gate arrivals (see br_stream_gate)
             St.graph = None
         else:
+            St.gate.zero_()
             St.tokens.fill_(pad_fill); St.finished.zero_(); St.step.zero_(); St.cur_len.copy_(cur0)
             if params.do_sample:
                 St.uniforms.copy_(uniforms)
@@ -323,6 +325,27 @@ class RolloutEngine:
             span = max(0, ch - 6) * pf_frac
             return (w, 6 + int(span * lo_frac), 6 + int(span * hi_frac))
 
+        # Stream gate (BR_STREAM_GATE=1): a GEMM that becomes resident while its predecessor GEMM is still streaming starts its early weight
+        # loads only when the predecessor's weights are on chip (see br_stream_gate).  `St.gate` counts arrivals; the targets are
+        # cumulative counts within a token step (the graph is replayed per step, the step counter supplies the epoch).
+        use_gate = os.environ.get("BR_STREAM_GATE", "0") not in ("0", "")
+        gate_plan = {}
+        if use_gate:
+            acc = 0
+            for li_, Lw_ in enumerate(Wd.layers):
+                for nm_ in ("w_qkv", "w_o", "w_gu", "w_down"):
+                    prev = acc if not (nm_ == "w_qkv" and li_ == 0) and nm_ != "w_o" else None     # after the embedding gather / the attention: HBM idles anyway
+                    acc += ops.skinny_grid(getattr(Lw_, nm_))
+                    gate_plan[(li_, nm_)] = prev
+            gate_plan["lm_head"] = acc
+            acc += ops.skinny_grid(Wd.lm_head)
+            gate_total = acc
+
+        def gate(key):
+            if not use_gate:
+                return None
+            return dict(counter=St.gate, epoch=step, epoch_base=1, per_step=gate_total, wait=gate_plan[key], signal=True)
+
         def decode_step_5():
             # 5 launches per layer: qkv GEMM (folded ln1), fused attention, o_proj (+res, sum x^2), gate/up GEMM (folded ln2, SwiGLU),
             # down_proj (+res, sum x^2); RMSNorm never launches in the decode loop.
@@ -331,14 +354,17 @@ class RolloutEngine:
             for li, Lw in enumerate(Wd.layers):
                 nxt_w = Wd.layers[li + 1].w_qkv if li + 1 < nl_ else Wd.lm_head
                 ops.skinny_gemm(h, Lw.w_qkv, scratch, out=b_qkv, sumsq_in=ssq_e if li == 0 else ssq_a, sumsq_in_n=1 if li == 0 else n_part, eps=eps,
-                                prefetch=stage(Lw.w_o, 0.0, 1.0))
+                                prefetch=stage(Lw.w_o, 0.0, 1.0), gate=gate((li, "w_qkv")))
                 ops.decode_attn_fused(b_qkv, Lw.q_norm, Lw.k_norm, kc[li], vc[li], table, cur_len, G, Hq, Hkv, D, n_shared, splits_shared,
                                       splits_private, theta, eps, ws, attn_out, rope=rope, prefetch=stage(Lw.w_gu, 0.0, 0.65))
-                ops.skinny_gemm(attn_out, Lw.w_o, scratch, mode=1, residual=h, out=b_x2, sumsq_out=ssq_b, prefetch=stage(Lw.w_gu, 0.65, 1.0))
-                ops.skinny_gemm(b_x2, Lw.w_gu, scratch, mode=2, out=b_act, sumsq_in=ssq_b, sumsq_in_n=n_part, eps=eps, prefetch=stage(Lw.w_down, 0.0, 1.0))
+                ops.skinny_gemm(attn_out, Lw.w_o, scratch, mode=1, residual=h, out=b_x2, sumsq_out=ssq_b, prefetch=stage(Lw.w_gu, 0.65, 1.0),
+                                gate=gate((li, "w_o")))
+                ops.skinny_gemm(b_x2, Lw.w_gu, scratch, mode=2, out=b_act, sumsq_in=ssq_b, sumsq_in_n=n_part, eps=eps, prefetch=stage(Lw.w_down, 0.0, 1.0),
+                                gate=gate((li, "w_gu")))
                 ops.skinny_gemm(b_act, Lw.w_down, scratch, mode=1, residual=b_x2, out=h, sumsq_out=ssq_a,
-                                prefetch=stage(nxt_w, 0.0, 1.0) if li + 1 < nl_ else (stage(nxt_w, 0.0, 0.1) if pf_frac > 0 else None))
-            ops.skinny_gemm(h, Wd.lm_head, scratch, mode=3, out=b_logits, sumsq_in=ssq_a, sumsq_in_n=n_part, eps=eps)
+                                prefetch=stage(nxt_w, 0.0, 1.0) if li + 1 < nl_ else (stage(nxt_w, 0.0, 0.1) if pf_frac > 0 else None),
+                                gate=gate((li, "w_down")))
+            ops.skinny_gemm(h, Wd.lm_head, scratch, mode=3, out=b_logits, sumsq_in=ssq_a, sumsq_in_n=n_part, eps=eps, gate=gate("lm_head"))
             sample(b_logits)
             ops.decode_advance(step, cur_len)
 
@@ -358,6 +384,7 @@ class RolloutEngine:
                 torch.cuda.current_stream().wait_stream(s)
                 for t, v in zip((tokens, next_ids, finished, step, cur_len), state):
                     t.copy_(v)                                                # the warm-up step is replayed for real below
+                St.gate.zero_()
                 St.graph = torch.cuda.CUDAGraph()
                 n0 = ops.LAUNCHES[0]
                 with torch.cuda.graph(St.graph):

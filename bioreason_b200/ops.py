@@ -251,6 +251,23 @@ def _l2_prefetch(spec):
     return pf, w
 
 
+def _gate(spec):
+    """dict(counter, epoch, epoch_base, per_step, wait (cumulative arrivals or None), signal (bool)) -> br_stream_gate* (or NULL)."""
+    if spec is None:
+        return ffi.NULL
+    g = ffi.new("br_stream_gate*")
+    g.counter = ptr(spec["counter"], "int32_t*"); g.epoch = ptr(spec["epoch"], "int32_t*")
+    g.epoch_base = int(spec.get("epoch_base", 0)); g.per_step = int(spec["per_step"])
+    g.wait_prefix = -1 if spec.get("wait") is None else int(spec["wait"])
+    g.signal = 1 if spec.get("signal", True) else 0
+    return g
+
+
+def skinny_grid(w) -> int:
+    """CTAs skinny_gemm launches for weight w [N, K]."""
+    return lib().br_skinny_grid(w.shape[0], w.shape[1])
+
+
 def skinny_chunk_units(w) -> int:
     """16 KB weight tiles one CTA of skinny_gemm streams for weight w [N, K] (the stream-K chunk; mirrors br_skinny_gemm_ex)."""
     n_sms = torch.cuda.get_device_properties(w.device).multi_processor_count
@@ -259,7 +276,7 @@ def skinny_chunk_units(w) -> int:
     return (units + grid - 1) // grid
 
 
-def skinny_gemm(x, w, scratch, *, mode=0, residual=None, out=None, sumsq_in=None, sumsq_in_n=1, sumsq_out=None, eps=0.0, prefetch=None):
+def skinny_gemm(x, w, scratch, *, mode=0, residual=None, out=None, sumsq_in=None, sumsq_in_n=1, sumsq_out=None, eps=0.0, prefetch=None, gate=None):
     """out[R, N] = x[R, K] @ w[N, K].T for R <= 32 decode rows (optionally with the folded-RMSNorm statistics).
     prefetch=(W_later, unit_lo, unit_hi): also stage tiles of a later GEMM of the chain into L2 (see br_l2_prefetch)."""
     _need_cuda(x, w)
@@ -271,10 +288,10 @@ def skinny_gemm(x, w, scratch, *, mode=0, residual=None, out=None, sumsq_in=None
         else:
             out = torch.empty(R, N // 2 if mode == 2 else N, device=x.device, dtype=torch.bfloat16)
     pf, _keep = _l2_prefetch(prefetch)
-    check(lib().br_skinny_gemm_pf(ptr(x), _row_major_2d(x), ptr(w), _row_major_2d(w), ptr(out), _row_major_2d(out), R, N, K, mode,
+    check(lib().br_skinny_gemm_gated(ptr(x), _row_major_2d(x), ptr(w), _row_major_2d(w), ptr(out), _row_major_2d(out), R, N, K, mode,
                                   ptr(residual), _row_major_2d(residual) if residual is not None else 0, ptr(scratch),
                                   ptr(sumsq_in, "float*"), int(sumsq_in_n) if sumsq_in is not None else 0, ptr(sumsq_out, "float*"),
-                                  float(eps), pf, _stream()),
+                                  float(eps), pf, _gate(gate), _stream()),
           "skinny_gemm")
     return out
 

@@ -144,6 +144,18 @@ typedef struct br_l2_prefetch { const void* W; int64_t ldw; int32_t N, K; int32_
 int br_skinny_gemm_pf(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
                       const void* residual, int64_t ldr, void* scratch, const float* sumsq_in, int sumsq_in_n, float* sumsq_out,
                       float eps, const br_l2_prefetch* prefetch, void* stream);
+/* Stream gate for the decode chain.  A decode GEMM that becomes resident early fills its weight ring BEFORE its dependency resolves; if
+ * the previous GEMM is still streaming, those loads only take bandwidth away from it (its exchange tail starts later by the same amount).
+ * With a gate the early loads start when the previous GEMM's weights have all ARRIVED, i.e. they run under its exchange tail, when HBM
+ * would idle.  `counter` (int32, zero at the start of a rollout) counts "my weights are on chip" arrivals, one per CTA of every gated
+ * launch; a launch starts prefetching once counter >= (*epoch - epoch_base) * per_step + wait_prefix (wait_prefix < 0: at once).  The
+ * gate is a timing hint only: the wait is bounded, and a wrong specification costs time, never correctness. */
+typedef struct br_stream_gate { int32_t* counter; const int32_t* epoch; int32_t epoch_base, per_step, wait_prefix, signal; } br_stream_gate;
+int br_skinny_gemm_gated(const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, int R, int N, int K, int mode,
+                         const void* residual, int64_t ldr, void* scratch, const float* sumsq_in, int sumsq_in_n, float* sumsq_out,
+                         float eps, const br_l2_prefetch* prefetch, const br_stream_gate* gate, void* stream);
+/* CTAs br_skinny_gemm launches for a weight [N, K] */
+int br_skinny_grid(int N, int K);
 /* Up to 4 dependent decode GEMMs in ONE persistent launch (e.g. o_proj -> gate/up -> down_proj -> next layer's qkv):
  * phases are separated by a grid-wide barrier inside the kernel and the weight producer prefetches across it, so the
  * HBM stream does not stall at layer boundaries.  Same per-phase semantics as br_skinny_gemm_ex. */

@@ -86,3 +86,25 @@ for who, m in (("none", 0), ("attn->gu", 8), ("attn->gu", 16), ("attn->gu", 24),
                                   prefetch=(w[tgt], 6, 6 + m) if tgt and m > 0 else None)
             x2 = k_o(w, x); a = k_gu(w, x2); x = k_down(w, a, x2)
     print(f"staging {who:10s} m={m:2d}: {timed(fn):7.2f} us per layer")
+
+# ---- stream gate (br_stream_gate): early weight loads start when the previous GEMM's weights are on chip
+cnt = torch.zeros(1, device=dev, dtype=torch.int32); ep = torch.ones(1, device=dev, dtype=torch.int32)
+grids = {k: ops.skinny_grid(ws[0][k]) for k in ("qkv", "o", "gu", "down")}
+per_layer = sum(grids.values())
+for mode in ("off", "on"):
+    def fn():
+        cnt.zero_()
+        x = x0
+        acc = 0
+        def g(name, wait):
+            nonlocal acc
+            spec = None if mode == "off" else dict(counter=cnt, epoch=ep, epoch_base=1, per_step=NL * per_layer, wait=(acc if wait else None), signal=True)
+            acc += grids[name]
+            return spec
+        for li, w in enumerate(ws):
+            q = ops.skinny_gemm(x, w["qkv"], scratch, sumsq_in=ssa, sumsq_in_n=n_part, eps=1e-6, gate=g("qkv", li > 0))
+            k_attn(q)
+            x2 = ops.skinny_gemm(attn_out, w["o"], scratch, mode=1, residual=x, sumsq_out=ssb, gate=g("o", False))
+            a = ops.skinny_gemm(x2, w["gu"], scratch, mode=2, sumsq_in=ssb, sumsq_in_n=n_part, eps=1e-6, gate=g("gu", True))
+            x = ops.skinny_gemm(a, w["down"], scratch, mode=1, residual=x2, sumsq_out=ssa, gate=g("down", True))
+    print(f"stream gate {mode:3s} (BR_SKINNY_PARK={os.environ.get('BR_SKINNY_PARK', '0')}): {timed(fn):7.2f} us per layer")
