@@ -200,9 +200,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (row_ok) {
             const uint4* op = reinterpret_cast<const uint4*>(p.o + tok * p.ldo + (long long)h * D + col0);
             const uint4* dp = reinterpret_cast<const uint4*>(p.dout + tok * p.lddo + (long long)h * D + col0);
-#pragma unroll 4
+            uint4 av[D / 16], gv[D / 16];                          // all 16 loads of the row in flight at once: this prologue runs with nothing
+#pragma unroll                                                   // else resident on the SM, every dependent round trip is exposed
+            for (int c = 0; c < D / 16; ++c) { av[c] = __ldg(op + c); gv[c] = __ldg(dp + c); }
+#pragma unroll
             for (int c = 0; c < D / 16; ++c) {
-                const uint4 a = __ldg(op + c), gd = __ldg(dp + c);
+                const uint4 a = av[c], gd = gv[c];
                 const float2 a0 = br::unpack_bf16(a.x), a1 = br::unpack_bf16(a.y), a2 = br::unpack_bf16(a.z), a3 = br::unpack_bf16(a.w);
                 const float2 g0 = br::unpack_bf16(gd.x), g1 = br::unpack_bf16(gd.y), g2 = br::unpack_bf16(gd.z), g3 = br::unpack_bf16(gd.w);
                 delta += a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y + a3.x * g3.x + a3.y * g3.y;
