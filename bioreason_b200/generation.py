@@ -83,6 +83,20 @@ def group_size_from_flags(eq: List[bool]) -> int:
     return 1
 
 
+def stream_gate_plan(layer_grids, lm_head_grid):
+    """Wait targets of the optional stream gate (br_stream_gate) for one token step.  layer_grids: per layer {w_qkv, w_o, w_gu, w_down: CTAs
+    of that launch}.  Every gated launch adds its grid to one counter when its weights are on chip; a launch waits for the cumulative count
+    of everything launched before it -- except the first qkv GEMM of a step (follows the embedding gather) and every o_proj (follows the
+    attention): HBM idles before those anyway.  Returns ({(layer, name) | "lm_head": target or None}, arrivals per step)."""
+    plan, acc = {}, 0
+    for li, grids in enumerate(layer_grids):
+        for nm in ("w_qkv", "w_o", "w_gu", "w_down"):
+            plan[(li, nm)] = None if (nm == "w_o" or (nm == "w_qkv" and li == 0)) else acc
+            acc += int(grids[nm])
+    plan["lm_head"] = acc
+    return plan, acc + int(lm_head_grid)
+
+
 def plan_pages(plen: List[int], G: int, C: int):
     """KV page plan of a rollout (host side, pure).  plen[u] = prompt length of unique prompt u; every prompt is sampled G times
     for C new tokens.  Full prompt pages (the first n_shared of every group; one count for all groups) are shared by the G rows
@@ -329,17 +343,10 @@ class RolloutEngine:
         # loads only when the predecessor's weights are on chip (see br_stream_gate).  `St.gate` counts arrivals; the targets are
         # cumulative counts within a token step (the graph is replayed per step, the step counter supplies the epoch).
         use_gate = os.environ.get("BR_STREAM_GATE", "0") not in ("0", "")
-        gate_plan = {}
+        gate_plan, gate_total = {}, 0
         if use_gate:
-            acc = 0
-            for li_, Lw_ in enumerate(Wd.layers):
-                for nm_ in ("w_qkv", "w_o", "w_gu", "w_down"):
-                    prev = acc if not (nm_ == "w_qkv" and li_ == 0) and nm_ != "w_o" else None     # after the embedding gather / the attention: HBM idles anyway
-                    acc += ops.skinny_grid(getattr(Lw_, nm_))
-                    gate_plan[(li_, nm_)] = prev
-            gate_plan["lm_head"] = acc
-            acc += ops.skinny_grid(Wd.lm_head)
-            gate_total = acc
+            gate_plan, gate_total = stream_gate_plan([{nm_: ops.skinny_grid(getattr(Lw_, nm_)) for nm_ in ("w_qkv", "w_o", "w_gu", "w_down")}
+                                                      for Lw_ in Wd.layers], ops.skinny_grid(Wd.lm_head))
 
         def gate(key):
             if not use_gate:
